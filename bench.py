@@ -1,0 +1,325 @@
+#!/usr/bin/env python3
+"""bench.py -- headline benchmark of the luBatchedInplace hot path on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+                    [--n 32] [--batch 1000000] [--dtype f32|f64] [--mode parallel|serial|none]
+
+Workload (BASELINE.json `metric`): matrices inverted per second, N=32, batch 1,000,000
+per GPU, fp32, parallel pivoting; synthetic distinct uniform(0,1) matrices.  A "step" is
+one in-place inversion of the whole batch (one kernel launch).  Successive steps invert
+the previous step's output (A -> A^-1 -> A ...): every step is a full-size inversion of
+valid data, and the 4 GB working set is far larger than L2, so no flush is needed.
+
+One JSON line is printed by rank 0 (see the keys below).  `--impl reference` times the
+reference algorithm's CPU restatement (oracle/, OpenMP over all host cores) on a bounded
+sample of the same workload -- the reference has no CPU implementation of its own for
+LU/inverse (verify.hpp only checks), and its GPU kernels are not a CPU arm.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "matrices_inverted_per_sec"
+UNIT = "matrices/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--n", type=int, default=32)
+    ap.add_argument("--batch", type=int, default=1_000_000, help="matrices per GPU")
+    ap.add_argument("--dtype", default="f32", choices=["f32", "f64"])
+    ap.add_argument("--mode", default="parallel", choices=["none", "serial", "parallel"])
+    ap.add_argument("--threads", type=int, default=0, help="NUMTHREADS knob (0 = library default)")
+    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--cpu-seconds", type=float, default=12.0, help="target CPU-baseline sample time")
+    ap.add_argument("--no-cublas", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+def workload_name(a):
+    return "N=%d batch=%d/GPU %s pivot=%s in-place inverse (BASELINE metric config)" % (a.n, a.batch, a.dtype, a.mode)
+
+
+def algorithmic_bytes(n, batch, esize, with_piv=False):
+    """one read + one in-place write of every matrix (+ 4N if piv stored)."""
+    return batch * (2 * n * n * esize + (4 * n if with_piv else 0))
+
+
+# ------------------------------------------------------------------------------------------
+# CPU arm: the oracle port on the host cores
+# ------------------------------------------------------------------------------------------
+
+def cpu_baseline(a, target_s):
+    from oracle import oracle as O  # cpu_baseline leg: the one place bench.py may run oracle/
+
+    dt = np.float32 if a.dtype == "f32" else np.float64
+    mode = {"none": 0, "serial": 1, "parallel": 2}[a.mode]
+    cores = O.max_threads()
+    rng = np.random.default_rng(32)
+    probe = rng.uniform(0, 1, size=(2000, a.n, a.n)).astype(dt)
+    t0 = time.perf_counter()
+    O.lu_batched_inplace_timed(probe, mode)
+    rate = 2000 / max(time.perf_counter() - t0, 1e-6)
+    sample = int(min(a.batch, max(2000, rate * target_s)))
+    X = rng.uniform(0, 1, size=(sample, a.n, a.n)).astype(dt)
+    t0 = time.perf_counter()
+    used = O.lu_batched_inplace_timed(X, mode)
+    dt_s = time.perf_counter() - t0
+    return {"value": sample / dt_s, "unit": UNIT, "cores": used, "kind": "port",
+            "sample": "%d distinct uniform(0,1) %dx%d %s matrices, pivot=%s, oracle/lu_oracle.c (C restatement of the "
+                      "reference algorithm, OpenMP static over the batch), %.1f s" % (sample, a.n, a.n, a.dtype, a.mode, dt_s),
+            "seconds": dt_s, "host_cores_total": os.cpu_count(), "sample_matrices": sample}
+
+
+def run_reference_arm(a):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    steps, warm = max(1, a.steps), max(0, a.warmup)
+    # bounded: whole run (warm-up + steps) within a few minutes
+    per_step = max(1.0, min(a.cpu_seconds, 150.0 / (steps + warm)))
+    vals = []
+    cb = None
+    for i in range(warm + steps):
+        cb = cpu_baseline(a, per_step)
+        if i >= warm:
+            vals.append((cb["sample_matrices"], cb["seconds"]))
+    tot_m = sum(v[0] for v in vals)
+    tot_s = sum(v[1] for v in vals)
+    value = tot_m / tot_s
+    cb["value"] = value
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": a.gpus, "steps": steps, "warmup": warm,
+            "ms_per_step": 1e3 * tot_s / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": a.dtype, "data": "synthetic", "impl": "reference",
+            "config": {"workload": workload_name(a), "note": "CPU arm: each step is a bounded sample of the workload"},
+            "cpu_baseline": cb,
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+# ------------------------------------------------------------------------------------------
+# clocks sampler
+# ------------------------------------------------------------------------------------------
+
+class Clocks:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "25"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.perf_counter(), line.strip()))
+
+    def stop(self, t0, t1):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], None, set()
+        rows = [r for t, r in self.rows if t0 <= t <= t1] or [r for _, r in self.rows[-3:]]
+        for r in rows:
+            f = [x.strip() for x in r.split(",")]
+            try:
+                sm.append(float(f[1])); mx = float(f[2])
+            except Exception:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(rows)}
+
+
+# ------------------------------------------------------------------------------------------
+# our arm
+# ------------------------------------------------------------------------------------------
+
+def main():
+    a = parse()
+    if a.impl == "reference":
+        return run_reference_arm(a)
+
+    import torch
+    import torch.distributed as dist
+
+    import matrixinversion_b200 as lub
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the hot path has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    dev = torch.device("cuda", local)
+
+    tdt = torch.float32 if a.dtype == "f32" else torch.float64
+    esize = 4 if a.dtype == "f32" else 8
+    n, batch = a.n, a.batch
+    if a.threads:
+        lub.set_num_threads(a.threads)
+
+    g = torch.Generator(device=dev).manual_seed(1000 * n + rank)
+    A = torch.rand((batch, n, n), generator=g, device=dev, dtype=tdt)  # shard of rank: its own batch (weak scaling)
+    pristine_head = A[:4096].clone()
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # correctness guard on this very buffer before timing (device-side verifyInv on a slice)
+    chk = pristine_head.clone()
+    lub.lu_batched_inplace(chk, None, a.mode)
+    ok, bad, _ = lub.verify_inv(pristine_head, chk, 1e-3 if a.dtype == "f32" else 1e-8)
+
+    for _ in range(max(a.warmup, 0)):
+        lub.lu_batched_inplace(A, None, a.mode)
+    barrier()
+    vis = [v for v in os.environ.get("CUDA_VISIBLE_DEVICES", "").split(",") if v.strip()]
+    clocks = Clocks(vis[local] if local < len(vis) else local)
+    clocks.start()
+    time.sleep(0.3)
+    evs = [torch.cuda.Event(enable_timing=True) for _ in range(a.steps + 1)]
+    barrier()
+    t_wall0 = time.perf_counter()
+    evs[0].record()
+    for i in range(a.steps):
+        lub.lu_batched_inplace(A, None, a.mode)   # launched on torch's current stream
+        evs[i + 1].record()
+    barrier()
+    t_wall1 = time.perf_counter()
+    ck = clocks.stop(t_wall0, t_wall1)
+    total_ms = evs[0].elapsed_time(evs[-1])
+    per = [evs[i].elapsed_time(evs[i + 1]) for i in range(a.steps)]
+    t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms_max = float(t.item())
+    value = world * batch * a.steps / (total_ms_max * 1e-3)
+
+    # ---- e2e: public API with HOST (pinned) buffers, copies inside the timed region ------
+    e2e = None
+    if not a.no_e2e:
+        hbuf = torch.empty((batch, n, n), dtype=tdt, pin_memory=True)
+        hbuf.copy_(torch.rand((batch, n, n), generator=g, device=dev, dtype=tdt))
+        H = hbuf.numpy()
+        lub.lu_batched_inplace(H, None, a.mode)  # warm-up (allocates the pipeline's device chunks)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(a.e2e_steps):
+            lub.lu_batched_inplace(H, None, a.mode)  # H2D chunks -> kernels -> D2H chunks, synchronous
+        barrier()
+        dt_e = time.perf_counter() - t0
+        te = torch.tensor([dt_e], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        e2e = {"value": world * batch * a.e2e_steps / float(te.item()), "unit": UNIT,
+               "h2d_bytes_per_step": batch * n * n * esize, "d2h_bytes_per_step": batch * n * n * esize,
+               "steps": a.e2e_steps, "api": "matrixinversion_b200.lu_batched_inplace(numpy pinned) -> lu_batched_inplace_host"}
+        del hbuf, H
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
+
+    # ---- roofline for the one kernel of the step ---------------------------------------------
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    else:
+        peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+    avg_ms = float(np.mean(per))
+    abytes = algorithmic_bytes(n, batch, esize)
+    achieved = abytes / (avg_ms * 1e-3) / 1e9
+    traffic = None
+    prof = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(prof):
+        try:
+            traffic = json.load(open(prof)).get("n%d_%s_%s" % (n, a.dtype, a.mode), {}).get("dram_bytes_per_launch")
+        except Exception:
+            traffic = None
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": traffic, "peak_source": peak_src, "kernel": "lub_invert_kernel<%s,N=%d,mode=%s>" % (a.dtype, n, a.mode),
+                "algorithmic_bytes_per_launch": abytes, "avg_launch_ms": avg_ms,
+                "frac_of_8TBps_nominal": achieved / 8000.0,
+                "gflops_2n3": 2.0 * n ** 3 * batch / (avg_ms * 1e-3) / 1e9}
+
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
+            "ms_per_step": total_ms_max / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": a.dtype, "data": "synthetic", "impl": "ours",
+            "config": {"workload": workload_name(a), "n": n, "batch_per_gpu": batch, "pivot_mode": a.mode,
+                       "parallelism": "batch sharded by contiguous slices, %d rank(s), no collective" % world,
+                       "l2": "working set %.2f GB per GPU >> 126 MB L2, no flush needed" % (batch * n * n * esize / 1e9),
+                       "geometry": vars(lub.geometry(n, batch, a.mode, np.float32 if a.dtype == "f32" else np.float64)),
+                       "precheck_verifyInv_first4096": {"correct": ok, "incorrect": bad}},
+            "clocks": ck, "e2e": e2e, "gpu_launches": a.steps, "roofline": roofline}
+
+    if not a.no_cublas:
+        try:
+            import ctypes
+            from matrixinversion_b200 import _lib
+            C = _lib.cublas_lib()
+            src = torch.rand((batch, n, n), generator=g, device=dev, dtype=tdt)
+            dst = torch.empty_like(src)
+            t1, t2 = ctypes.c_float(), ctypes.c_float()
+            best = None
+            for _ in range(3):
+                src.copy_(torch.rand((batch, n, n), generator=g, device=dev, dtype=tdt))  # getrf overwrites its input
+                rc = C.lu_batched_cublas_baseline(src.data_ptr(), dst.data_ptr(), n, batch, 0 if a.dtype == "f32" else 1, 1,
+                                                  ctypes.byref(t1), ctypes.byref(t2))
+                if rc != 0:
+                    raise RuntimeError("cublas rc=%d" % rc)
+                tot = t1.value + t2.value
+                if best is None or tot < best[0]:
+                    best = (tot, t1.value, t2.value)
+            line["cublas"] = {"value": batch / (best[0] * 1e-3), "unit": UNIT, "ms_getrf": best[1], "ms_getri": best[2],
+                              "what": "cublas%sgetrfBatched(pivoting)+getriBatched, same box, best of 3" % ("S" if a.dtype == "f32" else "D"),
+                              "speedup_ours_over_cublas": (batch / (avg_ms * 1e-3)) / (batch / (best[0] * 1e-3))}
+            del src, dst
+        except Exception as e:  # the comparison baseline is optional, the product is not
+            line["cublas"] = {"error": str(e)}
+
+    if world == 1 and not a.no_cpu:
+        line["cpu_baseline"] = cpu_baseline(a, a.cpu_seconds)
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -1,0 +1,133 @@
+/*
+ * lubatched.h -- C ABI of the B200-native batched small-matrix inversion library
+ * (liblubatched.so).  Plain pointers and sizes only; no torch / C++ types.
+ *
+ * The reference (sumukhashridhar/matrixInversion) has no library API: its operator
+ * boundary is the templated kernel launch
+ *     batched_lu_subwarp<FpType, N, TPM, MPB, B><<<numBlocks, T, shMem>>>(d_A)
+ * inside a per-configuration executable (templated/luBatchedInplace.cu:76,
+ * serial_pivot/luBatchedInplace.cu:105, parallel_pivot/luBatchedInplace.cu:127) whose
+ * knobs are the compile-time macros MATRIXSIZE / NUMMATRICES / NUMTHREADS
+ * (templated/luBatchedInplace.cu:4-6) and whose dtype is `using FpType`
+ * (templated/verify.hpp:9-10).  Every entry point below names the piece of that
+ * executable it replaces.  All knobs are runtime arguments here.
+ *
+ * Data layout (same as the reference, templated/luBatchedInplace.cuh:89-97):
+ *     T A[batch][n][n], row-major, contiguous, matrix b at element offset b*n*n,
+ * inverted IN PLACE.  n in [1, 32].
+ */
+#ifndef LUBATCHED_H_
+#define LUBATCHED_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* pivot_mode: which reference variant's semantics to reproduce */
+#define LUB_PIVOT_NONE 0     /* templated/luBatchedInplace.cuh:78-126 */
+#define LUB_PIVOT_SERIAL 1   /* serial_pivot/luBatchedInplace.cuh:104-167 (find_pivot :22-36) */
+#define LUB_PIVOT_PARALLEL 2 /* parallel_pivot/luBatchedInplace.cuh:127-199 (find_pivot_parallel :12-44,
+                                including the candidates its tree drops for non-power-of-two N) */
+/* dtype: the reference's FpType switch (templated/verify.hpp:9-10) */
+#define LUB_DTYPE_F32 0
+#define LUB_DTYPE_F64 1
+
+/* error codes (the reference's CUDA_CHECK prints and exit(1)s, templated/luBatchedInplace.cuh:9;
+ * this library never exits) */
+#define LUB_OK 0
+#define LUB_ERR_BAD_N (-1)
+#define LUB_ERR_BAD_MODE (-2)
+#define LUB_ERR_BAD_DTYPE (-3)
+#define LUB_ERR_BAD_ARG (-4)
+#define LUB_ERR_CUDA (-5)
+#define LUB_ERR_NO_DEVICE (-6)
+#define LUB_ERR_IO (-7)
+
+/* ---------------------------------------------------------------------------------------
+ * The hot path.  Replaces the kernel launch + its launch-geometry block
+ * (parallel_pivot/luBatchedInplace.cu:8-11,118-129).
+ *
+ *   ptr    DEVICE pointer to T[batch][n][n]; overwritten by the inverses.
+ *   piv    DEVICE pointer to int32[batch][n] or NULL.  When non-NULL receives the
+ *          reference's permutation vector (shared-memory `pivots[]`,
+ *          parallel_pivot/luBatchedInplace.cuh:140,146-148,161-168, never exported
+ *          upstream): piv[b][i] = original row index sitting in row i after all swaps.
+ *          pivot_mode NONE writes the identity.
+ *   n, batch, pivot_mode, dtype   as above; batch may be 0.
+ *
+ * Asynchronous on the library's current stream for the current device (see
+ * lu_batched_set_stream); returns LUB_OK or a negative error code.  No CPU fallback
+ * exists: without a CUDA device the call fails with LUB_ERR_NO_DEVICE / LUB_ERR_CUDA.
+ */
+int lu_batched_inplace(void* ptr, int32_t* piv, int n, int64_t batch, int pivot_mode, int dtype);
+
+/* Same, on an explicit stream (a cudaStream_t passed as void*; NULL = legacy default). */
+int lu_batched_inplace_stream(void* ptr, int32_t* piv, int n, int64_t batch, int pivot_mode, int dtype,
+                              void* stream);
+
+/* Stream used by lu_batched_inplace and the helpers below on the calling thread
+ * (the reference compiles with --default-stream per-thread, templated/run.py:48). */
+int lu_batched_set_stream(void* stream);
+
+/* HOST-pointer convenience replacing main()'s cudaMalloc + H2D + launch + D2H sequence
+ * (parallel_pivot/luBatchedInplace.cu:112-135): `host_ptr`/`host_piv` are host buffers
+ * (pinned or pageable); the batch is cut into chunks that are copied in, inverted and
+ * copied out on rotating streams so transfers overlap the kernels.  Synchronous. */
+int lu_batched_inplace_host(void* host_ptr, int32_t* host_piv, int n, int64_t batch, int pivot_mode,
+                            int dtype);
+
+/* NUMTHREADS knob (templated/luBatchedInplace.cu:6; table templated/run.py:201-223):
+ * threads per block for subsequent launches, a multiple of 32 in [32, 256];
+ * 0 restores the library's per-(n, dtype) default. */
+int lu_batched_set_threads(int numthreads);
+int lu_batched_get_threads(int n, int dtype);
+
+/* Launch geometry the library would use -- the numbers main() prints
+ * ("Threads per matrix", "Matrices per block", "Number of blocks",
+ * parallel_pivot/luBatchedInplace.cu:13-18). */
+int lu_batched_geometry(int n, int64_t batch, int pivot_mode, int dtype, int* threads_per_block,
+                        int* threads_per_matrix, int* matrices_per_block, int64_t* num_blocks,
+                        int* dyn_smem_bytes);
+
+/* Event-timed kernel time of the most recent lu_batched_inplace* call on this thread, in
+ * milliseconds, kernel only (the reference's "Kernel execution time",
+ * templated/luBatchedInplace.cu:71-82).  Timing is recorded only after
+ * lu_batched_enable_timing(1); the query synchronises on the stop event. */
+int lu_batched_enable_timing(int on);
+float lu_batched_last_kernel_ms(void);
+
+/* verify.hpp-compatible residual check (verifyInv, templated/verify.hpp:50-103) on HOST
+ * buffers: r(i,j) = sum_l A[j][l]*Ainv[l][i] accumulated in T; a matrix is correct iff
+ * every |r - delta_ij| < thr (the reference hard-codes thr = 1e-3).  Outputs may be NULL. */
+int lu_batched_verify_inv(const void* A, const void* Ainv, int n, int64_t batch, int dtype, double thr,
+                          int64_t* n_correct, int64_t* n_incorrect, double* max_abs_dev);
+
+/* Same predicate evaluated on the DEVICE (buffers are device pointers); used by the sweep
+ * driver so that a 1M-matrix check does not need two 4 GB host copies
+ * (parallel_pivot/luBatchedInplace.cu:158 passes its vectors by value). */
+int lu_batched_verify_inv_device(const void* dA, const void* dAinv, int n, int64_t batch, int dtype,
+                                 double thr, int64_t* n_correct, int64_t* n_incorrect,
+                                 double* max_abs_dev);
+
+/* Text input with the reference's semantics (templated/luBatchedInplace.cu:27-34): the
+ * first `count` whitespace-separated tokens of `path`, parsed as T -- a PREFIX of the
+ * token stream, not a sub-block.  Returns LUB_OK, or LUB_ERR_IO if the file is missing
+ * or holds fewer tokens. */
+int lu_batched_read_tokens(const char* path, void* out, int64_t count, int dtype);
+
+/* main()'s replicate loop (templated/luBatchedInplace.cu:46-57): fill dst[batch][n][n]
+ * (HOST) with copies of tmpl[n][n]. */
+int lu_batched_replicate(const void* tmpl, void* dst, int n, int64_t batch, int dtype);
+
+/* Device facts (deviceProps.cu:4-23): SM count, max dynamic smem per block, clock kHz. */
+int lu_batched_device_info(int* sm_count, int* max_smem_optin, int* clock_khz, int* cc_major, int* cc_minor);
+
+const char* lu_batched_last_error(void);
+const char* lu_batched_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LUBATCHED_H_ */

@@ -1,0 +1,282 @@
+"""Host-side mirror of the reference's operator boundary for the luBatchedInplace path.
+
+The reference has no importable API: each variant directory holds a `main()`
+(`/root/reference/<variant>/luBatchedInplace.cu`) that reads a template matrix, replicates
+it, copies it to the device, launches `batched_lu_subwarp` once, times it with CUDA events,
+copies back and runs `verifyInv`.  The functions below are those steps, one per function,
+with the same names / argument meaning where the reference has a name, all thin wrappers
+over the C ABI in include/lubatched.h (no arithmetic happens in Python and there is no
+CPU fallback: the CUDA library must load and a GPU must be present for every compute call).
+
+    variant dir        pivot_mode
+    templated/         "none"      (0)
+    serial_pivot/      "serial"    (1)
+    parallel_pivot/    "parallel"  (2)
+"""
+from __future__ import annotations
+
+import ctypes
+import sys
+import time
+from dataclasses import dataclass
+
+import numpy as np
+
+from . import _lib
+from ._lib import DTYPE_F32, DTYPE_F64, PIVOT_NONE, PIVOT_PARALLEL, PIVOT_SERIAL, LubError, check
+
+PIVOT_MODES = {"none": PIVOT_NONE, "serial": PIVOT_SERIAL, "parallel": PIVOT_PARALLEL,
+               "templated": PIVOT_NONE, "serial_pivot": PIVOT_SERIAL, "parallel_pivot": PIVOT_PARALLEL}
+
+
+def _mode(pivot_mode) -> int:
+    if isinstance(pivot_mode, str):
+        try:
+            return PIVOT_MODES[pivot_mode]
+        except KeyError:
+            raise LubError(-2, "unknown pivot_mode %r" % (pivot_mode,)) from None
+    return int(pivot_mode)
+
+
+def _dtype_code(dtype) -> int:
+    try:
+        import torch
+        if isinstance(dtype, torch.dtype):
+            return {torch.float32: DTYPE_F32, torch.float64: DTYPE_F64}[dtype]
+    except KeyError:
+        raise LubError(-3, "dtype must be float32 or float64") from None
+    except ImportError:
+        pass
+    dt = np.dtype(dtype)
+    if dt == np.float32:
+        return DTYPE_F32
+    if dt == np.float64:
+        return DTYPE_F64
+    raise LubError(-3, "dtype must be float32 or float64")
+
+
+def _is_torch(x) -> bool:
+    return type(x).__module__.startswith("torch")
+
+
+def _check_batch(shape):
+    if len(shape) != 3 or shape[1] != shape[2]:
+        raise LubError(-4, "expected a [batch, n, n] array, got shape %s" % (tuple(shape),))
+    return int(shape[0]), int(shape[1])
+
+
+# ------------------------------------------------------------------------------------------
+# the hot path
+# ------------------------------------------------------------------------------------------
+
+def lu_batched_inplace(A, piv=None, pivot_mode="parallel", stream=None):
+    """Invert every matrix of A[batch, n, n] in place (the `batched_lu_subwarp` launch,
+    parallel_pivot/luBatchedInplace.cu:127).
+
+    A: contiguous CUDA torch tensor (float32/float64) -> asynchronous launch on `stream`
+       (default: torch's current stream); or a C-contiguous numpy array -> the chunked
+       host pipeline (`lu_batched_inplace_host`), synchronous.
+    piv: optional int32 [batch, n] buffer of the same kind; receives the reference's
+       permutation vector (`pivots[]`, parallel_pivot/luBatchedInplace.cuh:140,161-168).
+    Returns A.
+    """
+    L = _lib.lib()
+    mode = _mode(pivot_mode)
+    batch, n = _check_batch(A.shape)
+    if _is_torch(A):
+        import torch
+        if not A.is_cuda:
+            raise LubError(-4, "torch tensors must live on a CUDA device (pass numpy for host data)")
+        if not A.is_contiguous():
+            raise LubError(-4, "A must be contiguous")
+        dt = _dtype_code(A.dtype)
+        pptr = None
+        if piv is not None:
+            if not (piv.is_cuda and piv.is_contiguous() and piv.dtype == torch.int32 and tuple(piv.shape) == (batch, n)):
+                raise LubError(-4, "piv must be a contiguous CUDA int32 [batch, n] tensor")
+            pptr = piv.data_ptr()
+        with torch.cuda.device(A.device):
+            s = stream if stream is not None else torch.cuda.current_stream(A.device)
+            sp = s.cuda_stream if hasattr(s, "cuda_stream") else int(s)
+            check(L.lu_batched_inplace_stream(A.data_ptr(), pptr, n, batch, mode, dt, sp))
+        return A
+    if not isinstance(A, np.ndarray) or not A.flags.c_contiguous or not A.flags.writeable:
+        raise LubError(-4, "A must be a CUDA torch tensor or a writable C-contiguous numpy array")
+    dt = _dtype_code(A.dtype)
+    pptr = None
+    if piv is not None:
+        if not (isinstance(piv, np.ndarray) and piv.dtype == np.int32 and piv.shape == (batch, n) and piv.flags.c_contiguous):
+            raise LubError(-4, "piv must be a C-contiguous int32 [batch, n] numpy array")
+        pptr = piv.ctypes.data
+    check(L.lu_batched_inplace_host(A.ctypes.data, pptr, n, batch, mode, dt))
+    return A
+
+
+def lu_batched_inplace_ptr(ptr: int, piv_ptr, n: int, batch: int, pivot_mode, dtype, stream_ptr: int = 0) -> None:
+    """Raw-pointer form: exactly the C ABI call (device pointers as integers)."""
+    check(_lib.lib().lu_batched_inplace_stream(ptr, piv_ptr, n, batch, _mode(pivot_mode), _dtype_code(dtype), stream_ptr))
+
+
+def set_num_threads(numthreads: int) -> None:
+    """NUMTHREADS knob (templated/luBatchedInplace.cu:6); 0 = library default."""
+    check(_lib.lib().lu_batched_set_threads(int(numthreads)))
+
+
+@dataclass
+class Geometry:
+    threads_per_block: int
+    threads_per_matrix: int
+    matrices_per_block: int
+    num_blocks: int
+    dyn_smem_bytes: int
+
+
+def geometry(n: int, batch: int, pivot_mode="parallel", dtype=np.float32) -> Geometry:
+    """Launch geometry -- the numbers main() prints (parallel_pivot/luBatchedInplace.cu:13-18)."""
+    tpb, tpm, mpb, smem = ctypes.c_int(), ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
+    nb = ctypes.c_int64()
+    check(_lib.lib().lu_batched_geometry(n, batch, _mode(pivot_mode), _dtype_code(dtype), ctypes.byref(tpb),
+                                         ctypes.byref(tpm), ctypes.byref(mpb), ctypes.byref(nb), ctypes.byref(smem)))
+    return Geometry(tpb.value, tpm.value, mpb.value, nb.value, smem.value)
+
+
+def enable_timing(on: bool = True) -> None:
+    check(_lib.lib().lu_batched_enable_timing(int(on)))
+
+
+def last_kernel_ms() -> float:
+    """The reference's "Kernel execution time" (templated/luBatchedInplace.cu:71-82)."""
+    return float(_lib.lib().lu_batched_last_kernel_ms())
+
+
+def device_info() -> dict:
+    """deviceProps.cu:4-23."""
+    v = [ctypes.c_int() for _ in range(5)]
+    check(_lib.lib().lu_batched_device_info(*[ctypes.byref(x) for x in v]))
+    return dict(zip(("sm_count", "max_smem_optin", "clock_khz", "cc_major", "cc_minor"), (x.value for x in v)))
+
+
+# ------------------------------------------------------------------------------------------
+# verify.hpp-compatible check
+# ------------------------------------------------------------------------------------------
+
+def verify_inv(A, A_inv, thr: float = 1e-3):
+    """verifyInv (templated/verify.hpp:50-103): returns (correct, incorrect, max |r - delta|).
+
+    numpy arrays are checked by the library's host code, CUDA tensors on the device.
+    """
+    L = _lib.lib()
+    batch, n = _check_batch(A.shape)
+    ok, bad, dev = ctypes.c_int64(), ctypes.c_int64(), ctypes.c_double()
+    if _is_torch(A):
+        if not (A.is_cuda and A_inv.is_cuda and A.is_contiguous() and A_inv.is_contiguous() and A.dtype == A_inv.dtype):
+            raise LubError(-4, "A and A_inv must be contiguous CUDA tensors of one dtype")
+        import torch
+        with torch.cuda.device(A.device):
+            check(L.lu_batched_set_stream(torch.cuda.current_stream(A.device).cuda_stream))
+            check(L.lu_batched_verify_inv_device(A.data_ptr(), A_inv.data_ptr(), n, batch, _dtype_code(A.dtype), thr,
+                                                 ctypes.byref(ok), ctypes.byref(bad), ctypes.byref(dev)))
+            check(L.lu_batched_set_stream(None))
+    else:
+        A = np.ascontiguousarray(A)
+        A_inv = np.ascontiguousarray(A_inv, dtype=A.dtype)
+        check(L.lu_batched_verify_inv(A.ctypes.data, A_inv.ctypes.data, n, batch, _dtype_code(A.dtype), thr,
+                                      ctypes.byref(ok), ctypes.byref(bad), ctypes.byref(dev)))
+    return ok.value, bad.value, dev.value
+
+
+# ------------------------------------------------------------------------------------------
+# inputs: mtrand*.txt / matrix.txt
+# ------------------------------------------------------------------------------------------
+
+def read_template(path: str, n: int, dtype=np.float32) -> np.ndarray:
+    """The template matrix as main() reads it (templated/luBatchedInplace.cu:27-34): the
+    first n*n whitespace-separated tokens of the file reshaped to [n, n] -- a prefix of the
+    token stream, NOT the top-left block of the 32-wide matrix."""
+    out = np.empty((n, n), dtype=dtype)
+    check(_lib.lib().lu_batched_read_tokens(str(path).encode(), out.ctypes.data, n * n, _dtype_code(dtype)))
+    return out
+
+
+def replicate(template: np.ndarray, batch: int) -> np.ndarray:
+    """main()'s fill loop (templated/luBatchedInplace.cu:46-57): batch copies of the template."""
+    template = np.ascontiguousarray(template)
+    n = template.shape[0]
+    out = np.empty((batch, n, n), dtype=template.dtype)
+    check(_lib.lib().lu_batched_replicate(template.ctypes.data, out.ctypes.data, n, batch, _dtype_code(template.dtype)))
+    return out
+
+
+def l1_norm(template: np.ndarray) -> float:
+    """What the reference prints as "Condition number of the matrix is:": its calc_cond_num
+    (templated/verify.hpp:188-281) reduces A to the identity without an augmented block and
+    therefore returns ||A||_1 * 1.  Kept so the stdout contract is unchanged."""
+    return float(np.abs(template).sum(axis=0).max().astype(template.dtype))
+
+
+# ------------------------------------------------------------------------------------------
+# main(): one run with the reference's stdout contract
+# ------------------------------------------------------------------------------------------
+
+def default_num_threads(n: int) -> int:
+    """The sweep's NUMTHREADS table (templated/run.py:201-223): largest multiple of n <= 32."""
+    return (32 // n) * n
+
+
+def run_main(matrix_size: int, num_matrices: int, num_threads: int = 0, pivot_mode="parallel",
+             input_file: str = "mtrand32_new1.txt", dtype=np.float32, template: np.ndarray | None = None,
+             out=sys.stdout, verify: bool = True, warm: bool = False) -> dict:
+    """One run of the reference executable (`./custom`), same stdout lines in the same order
+    (parallel_pivot/luBatchedInplace.cu:13-18,38,82,104-105,115,133,136,158-162), on this
+    library.  Returns the parsed numbers.  `num_threads` here is the library's threads per
+    block (0 = default); the reference's per-warp packing is chosen by the library.
+    """
+    import torch
+
+    n, batch = int(matrix_size), int(num_matrices)
+    mode = _mode(pivot_mode)
+    if num_threads:
+        set_num_threads(num_threads)
+    geo = geometry(n, batch, mode, dtype)
+    p = lambda *a: print(*a, file=out)
+    p("Matrix size:", n)
+    p("Number of matrices:", batch)
+    p("Number of threads per block:", geo.threads_per_block)
+    p("Threads per matrix:", geo.threads_per_matrix)
+    p("Matrices per block:", geo.matrices_per_block)
+    p("Number of blocks:", geo.num_blocks)
+    p("Reading data from file.")
+    if template is None:
+        template = read_template(input_file, n, dtype)
+    p("Condition number of the matrix is:", l1_norm(template))
+    t0 = time.perf_counter()
+    A = replicate(template, batch)
+    p("Time taken to read data: %g seconds" % (time.perf_counter() - t0))
+    p("Data read from file.")
+    dA = torch.from_numpy(A).cuda()
+    p("Data copied to device.")
+    if warm:
+        lu_batched_inplace(dA.clone(), None, mode)
+    enable_timing(True)
+    try:
+        lu_batched_inplace(dA, None, mode)
+        ms = last_kernel_ms()
+    finally:
+        enable_timing(False)
+        if num_threads:
+            set_num_threads(0)
+    p("Kernel execution time: %g milliseconds" % ms)
+    res = {"matrix_size": n, "num_matrices": batch, "num_threads": geo.threads_per_block, "kernel_ms": ms}
+    if verify:
+        t0 = time.perf_counter()
+        dOrig = torch.from_numpy(A).cuda()
+        ok, bad, dev = verify_inv(dOrig, dA)
+        p("Data copied back to host.")
+        p("Correct inversions:", ok)
+        p("Incorrect inversions:", bad)
+        p("Time taken to verify inverse: %g seconds" % (time.perf_counter() - t0))
+        res.update(correct=ok, incorrect=bad, max_abs_dev=dev)
+    else:
+        p("Data copied back to host.")
+    res["A_inv"] = dA
+    return res

@@ -1,0 +1,342 @@
+// lubatched_api.cu -- the C ABI of include/lubatched.h: argument checking, runtime dispatch
+// over what the reference fixes at compile time (MATRIXSIZE / NUMTHREADS / FpType,
+// templated/luBatchedInplace.cu:4-6, templated/verify.hpp:9-10), stream / timing state, the
+// chunked host-pointer pipeline, the verify.hpp-compatible residual check and the text
+// loader.  There is no CPU implementation of the inversion in this library.
+#include <cuda_runtime.h>
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <fstream>
+#include <string>
+#include <vector>
+
+#include "../../include/lubatched.h"
+#include "lub_launch.cuh"
+
+namespace lub {
+#define LUB_DECL(TN, M) \
+    LaunchFn lub_get_##TN##_m##M##_q0(int); LaunchFn lub_get_##TN##_m##M##_q1(int); \
+    LaunchFn lub_get_##TN##_m##M##_q2(int); LaunchFn lub_get_##TN##_m##M##_q3(int);
+LUB_DECL(f32, 0) LUB_DECL(f32, 1) LUB_DECL(f32, 2)
+LUB_DECL(f64, 0) LUB_DECL(f64, 1) LUB_DECL(f64, 2)
+#undef LUB_DECL
+
+static LaunchFn find_launcher(int n, int mode, int dtype) {
+    using Getter = LaunchFn (*)(int);
+#define LUB_ROW(TN, M) { lub_get_##TN##_m##M##_q0, lub_get_##TN##_m##M##_q1, lub_get_##TN##_m##M##_q2, lub_get_##TN##_m##M##_q3 }
+    static const Getter table[2][3][4] = {
+        { LUB_ROW(f32, 0), LUB_ROW(f32, 1), LUB_ROW(f32, 2) },
+        { LUB_ROW(f64, 0), LUB_ROW(f64, 1), LUB_ROW(f64, 2) },
+    };
+#undef LUB_ROW
+    return table[dtype][mode][(n - 1) / 8](n);
+}
+}  // namespace lub
+
+namespace {
+
+thread_local std::string g_err;
+thread_local cudaStream_t g_stream = nullptr;
+thread_local int g_threads = 0;
+thread_local bool g_timing = false;
+thread_local cudaEvent_t g_ev0 = nullptr, g_ev1 = nullptr;
+thread_local bool g_ev_valid = false;
+
+int fail(int code, const std::string& msg) {
+    g_err = msg;
+    return code;
+}
+int cuda_fail(cudaError_t e, const char* where) {
+    g_err = std::string(where) + ": " + cudaGetErrorString(e);
+    return (e == cudaErrorNoDevice || e == cudaErrorInsufficientDriver) ? LUB_ERR_NO_DEVICE : LUB_ERR_CUDA;
+}
+#define CU(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return cuda_fail(e_, #call); } while (0)
+
+int check_args(int n, int64_t batch, int mode, int dtype) {
+    if (n < 1 || n > 32) return fail(LUB_ERR_BAD_N, "n must be in [1, 32]");
+    if (mode < LUB_PIVOT_NONE || mode > LUB_PIVOT_PARALLEL) return fail(LUB_ERR_BAD_MODE, "pivot_mode must be 0 (none), 1 (serial) or 2 (parallel)");
+    if (dtype != LUB_DTYPE_F32 && dtype != LUB_DTYPE_F64) return fail(LUB_ERR_BAD_DTYPE, "dtype must be 0 (fp32) or 1 (fp64)");
+    if (batch < 0) return fail(LUB_ERR_BAD_ARG, "batch must be >= 0");
+    return LUB_OK;
+}
+
+size_t esize(int dtype) { return dtype == LUB_DTYPE_F32 ? 4 : 8; }
+
+int launch_on(void* ptr, int32_t* piv, int n, int64_t batch, int mode, int dtype, cudaStream_t s,
+              lub::LaunchInfo* info, int dry) {
+    int rc = check_args(n, batch, mode, dtype);
+    if (rc != LUB_OK) return rc;
+    if (!dry && batch > 0) {
+        if (ptr == nullptr) return fail(LUB_ERR_BAD_ARG, "ptr is NULL");
+        if (reinterpret_cast<uintptr_t>(ptr) % esize(dtype)) return fail(LUB_ERR_BAD_ARG, "ptr is not aligned to the element size");
+    }
+    lub::LaunchFn fn = lub::find_launcher(n, mode, dtype);
+    if (!fn) return fail(LUB_ERR_BAD_N, "no kernel for this n");
+    const bool timed = g_timing && !dry && batch > 0;
+    if (timed) {
+        if (!g_ev0) { CU(cudaEventCreate(&g_ev0)); CU(cudaEventCreate(&g_ev1)); }
+        CU(cudaEventRecord(g_ev0, s));
+    }
+    cudaError_t e = fn(ptr, piv, (long long)batch, g_threads, s, info, dry);
+    if (e != cudaSuccess) return cuda_fail(e, "kernel launch");
+    if (timed) { CU(cudaEventRecord(g_ev1, s)); g_ev_valid = true; }
+    return LUB_OK;
+}
+
+// ---- verify.hpp-compatible residual check ---------------------------------------------------
+
+template <typename T>
+void verify_host(const T* A, const T* X, int n, int64_t batch, double thr, int64_t* ok, int64_t* bad, double* dev) {
+    const T threshold = static_cast<T>(thr);
+    int64_t good = 0;
+    double worst = 0.0;
+    bool saw_nan = false;
+#pragma omp parallel for schedule(static) reduction(+ : good) reduction(max : worst) reduction(|| : saw_nan)
+    for (int64_t k = 0; k < batch; ++k) {
+        const T* a = A + k * (int64_t)n * n;
+        const T* x = X + k * (int64_t)n * n;
+        int id_cnt = 0, off_cnt = 0;
+        for (int i = 0; i < n; ++i)
+            for (int j = 0; j < n; ++j) {
+                T r = T(0);
+                for (int l = 0; l < n; ++l) r += a[j * n + l] * x[l * n + i];
+                const T d = (i == j) ? std::fabs(r - T(1)) : std::fabs(r);
+                if (d < threshold) (i == j ? id_cnt : off_cnt)++;
+                if (d != d) saw_nan = true;
+                else if ((double)d > worst) worst = (double)d;
+            }
+        if (id_cnt == n && off_cnt == n * (n - 1)) good++;
+    }
+    if (ok) *ok = good;
+    if (bad) *bad = batch - good;
+    if (dev) *dev = saw_nan ? NAN : worst;
+}
+
+template <typename T>
+__global__ void verify_kernel(const T* __restrict__ A, const T* __restrict__ X, int n, long long batch, T thr,
+                              unsigned long long* good, unsigned int* worst_bits, unsigned int* nan_flag) {
+    // one warp per matrix; lane handles entries e = lane, lane+32, ... of the n*n product
+    const int lane = threadIdx.x & 31;
+    const long long w = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const long long nw = ((long long)gridDim.x * blockDim.x) >> 5;
+    for (long long k = w; k < batch; k += nw) {
+        const T* a = A + k * (long long)n * n;
+        const T* x = X + k * (long long)n * n;
+        bool all_ok = true;
+        float worst = 0.f;
+        bool nan = false;
+        for (int e = lane; e < n * n; e += 32) {
+            const int i = e / n, j = e % n;
+            T r = T(0);
+            for (int l = 0; l < n; ++l) r += a[j * n + l] * x[l * n + i];
+            const T d = (i == j) ? fabs(r - T(1)) : fabs(r);
+            if (!(d < thr)) all_ok = false;
+            if (d != d) nan = true;
+            else worst = fmaxf(worst, (float)d);
+        }
+        all_ok = __all_sync(0xffffffffu, all_ok);
+        nan = __any_sync(0xffffffffu, nan);
+        for (int o = 16; o > 0; o >>= 1) worst = fmaxf(worst, __shfl_xor_sync(0xffffffffu, worst, o));
+        if (lane == 0) {
+            if (all_ok) atomicAdd(good, 1ull);
+            atomicMax(worst_bits, __float_as_uint(worst));
+            if (nan) atomicOr(nan_flag, 1u);
+        }
+    }
+}
+
+// ---- scratch buffers for the host-pointer pipeline ----------------------------------------
+
+struct HostPipe {
+    static constexpr int kSlots = 3;
+    void* buf[kSlots] = {nullptr, nullptr, nullptr};
+    int32_t* pbuf[kSlots] = {nullptr, nullptr, nullptr};
+    size_t cap = 0, pcap = 0;
+    cudaStream_t st[kSlots] = {nullptr, nullptr, nullptr};
+    int dev = -1;
+    void release() {
+        for (int i = 0; i < kSlots; ++i) {
+            if (buf[i]) cudaFree(buf[i]);
+            if (pbuf[i]) cudaFree(pbuf[i]);
+            if (st[i]) cudaStreamDestroy(st[i]);
+            buf[i] = nullptr; pbuf[i] = nullptr; st[i] = nullptr;
+        }
+        cap = pcap = 0; dev = -1;
+    }
+};
+thread_local HostPipe g_pipe;
+
+}  // namespace
+
+extern "C" {
+
+const char* lu_batched_version(void) { return "lubatched 0.1 (sm_100a)"; }
+const char* lu_batched_last_error(void) { return g_err.c_str(); }
+
+int lu_batched_set_stream(void* stream) {
+    g_stream = static_cast<cudaStream_t>(stream);
+    return LUB_OK;
+}
+
+int lu_batched_set_threads(int numthreads) {
+    if (numthreads != 0 && (numthreads < 32 || numthreads > lub::kMaxThreads || numthreads % 32))
+        return fail(LUB_ERR_BAD_ARG, "numthreads must be 0 or a multiple of 32 in [32, 256]");
+    g_threads = numthreads;
+    return LUB_OK;
+}
+
+int lu_batched_get_threads(int n, int dtype) {
+    (void)n; (void)dtype;
+    return g_threads ? g_threads : 128;
+}
+
+int lu_batched_enable_timing(int on) {
+    g_timing = on != 0;
+    g_ev_valid = false;
+    return LUB_OK;
+}
+
+float lu_batched_last_kernel_ms(void) {
+    if (!g_ev_valid) return -1.f;
+    if (cudaEventSynchronize(g_ev1) != cudaSuccess) return -1.f;
+    float ms = -1.f;
+    if (cudaEventElapsedTime(&ms, g_ev0, g_ev1) != cudaSuccess) return -1.f;
+    return ms;
+}
+
+int lu_batched_inplace_stream(void* ptr, int32_t* piv, int n, int64_t batch, int pivot_mode, int dtype, void* stream) {
+    return launch_on(ptr, piv, n, batch, pivot_mode, dtype, static_cast<cudaStream_t>(stream), nullptr, 0);
+}
+
+int lu_batched_inplace(void* ptr, int32_t* piv, int n, int64_t batch, int pivot_mode, int dtype) {
+    return launch_on(ptr, piv, n, batch, pivot_mode, dtype, g_stream, nullptr, 0);
+}
+
+int lu_batched_geometry(int n, int64_t batch, int pivot_mode, int dtype, int* threads_per_block,
+                        int* threads_per_matrix, int* matrices_per_block, int64_t* num_blocks, int* dyn_smem_bytes) {
+    lub::LaunchInfo info{};
+    int rc = launch_on(nullptr, nullptr, n, batch, pivot_mode, dtype, nullptr, &info, 1);
+    if (rc != LUB_OK) return rc;
+    if (threads_per_block) *threads_per_block = info.threads_per_block;
+    if (threads_per_matrix) *threads_per_matrix = info.threads_per_matrix;
+    if (matrices_per_block) *matrices_per_block = info.matrices_per_block;
+    if (num_blocks) *num_blocks = info.num_blocks;
+    if (dyn_smem_bytes) *dyn_smem_bytes = info.dyn_smem_bytes;
+    return LUB_OK;
+}
+
+int lu_batched_inplace_host(void* host_ptr, int32_t* host_piv, int n, int64_t batch, int pivot_mode, int dtype) {
+    int rc = check_args(n, batch, pivot_mode, dtype);
+    if (rc != LUB_OK) return rc;
+    if (batch == 0) return LUB_OK;
+    if (!host_ptr) return fail(LUB_ERR_BAD_ARG, "host_ptr is NULL");
+    const size_t mat_bytes = (size_t)n * n * esize(dtype);
+    // ~64 MiB chunks, a whole number of matrices, at least 3 chunks in flight when possible
+    int64_t chunk = std::max<int64_t>(1, (int64_t)((64ull << 20) / mat_bytes));
+    chunk = std::min<int64_t>(chunk, std::max<int64_t>(1, (batch + HostPipe::kSlots - 1) / HostPipe::kSlots));
+    int dev = 0;
+    CU(cudaGetDevice(&dev));
+    HostPipe& P = g_pipe;
+    if (P.dev != dev) P.release();
+    P.dev = dev;
+    const size_t need = (size_t)chunk * mat_bytes, pneed = host_piv ? (size_t)chunk * n * 4 : 0;
+    for (int i = 0; i < HostPipe::kSlots; ++i) {
+        if (!P.st[i]) CU(cudaStreamCreateWithFlags(&P.st[i], cudaStreamNonBlocking));
+        if (P.cap < need) { if (P.buf[i]) cudaFree(P.buf[i]); P.buf[i] = nullptr; CU(cudaMalloc(&P.buf[i], need)); }
+        if (P.pcap < pneed) { if (P.pbuf[i]) cudaFree(P.pbuf[i]); P.pbuf[i] = nullptr; CU(cudaMalloc((void**)&P.pbuf[i], pneed)); }
+    }
+    P.cap = std::max(P.cap, need);
+    P.pcap = std::max(P.pcap, pneed);
+    char* h = static_cast<char*>(host_ptr);
+    int slot = 0;
+    for (int64_t b0 = 0; b0 < batch; b0 += chunk, slot = (slot + 1) % HostPipe::kSlots) {
+        const int64_t nb = std::min<int64_t>(chunk, batch - b0);
+        cudaStream_t s = P.st[slot];
+        CU(cudaMemcpyAsync(P.buf[slot], h + (size_t)b0 * mat_bytes, (size_t)nb * mat_bytes, cudaMemcpyHostToDevice, s));
+        rc = launch_on(P.buf[slot], host_piv ? P.pbuf[slot] : nullptr, n, nb, pivot_mode, dtype, s, nullptr, 0);
+        if (rc != LUB_OK) return rc;
+        CU(cudaMemcpyAsync(h + (size_t)b0 * mat_bytes, P.buf[slot], (size_t)nb * mat_bytes, cudaMemcpyDeviceToHost, s));
+        if (host_piv) CU(cudaMemcpyAsync(host_piv + b0 * n, P.pbuf[slot], (size_t)nb * n * 4, cudaMemcpyDeviceToHost, s));
+    }
+    for (int i = 0; i < HostPipe::kSlots; ++i) CU(cudaStreamSynchronize(P.st[i]));
+    return LUB_OK;
+}
+
+int lu_batched_verify_inv(const void* A, const void* Ainv, int n, int64_t batch, int dtype, double thr,
+                          int64_t* n_correct, int64_t* n_incorrect, double* max_abs_dev) {
+    if (n < 1 || n > 1024) return fail(LUB_ERR_BAD_N, "n out of range");
+    if (batch < 0 || (!A && batch) || (!Ainv && batch)) return fail(LUB_ERR_BAD_ARG, "bad buffers");
+    if (dtype == LUB_DTYPE_F32) verify_host(static_cast<const float*>(A), static_cast<const float*>(Ainv), n, batch, thr, n_correct, n_incorrect, max_abs_dev);
+    else if (dtype == LUB_DTYPE_F64) verify_host(static_cast<const double*>(A), static_cast<const double*>(Ainv), n, batch, thr, n_correct, n_incorrect, max_abs_dev);
+    else return fail(LUB_ERR_BAD_DTYPE, "dtype must be 0 or 1");
+    return LUB_OK;
+}
+
+int lu_batched_verify_inv_device(const void* dA, const void* dAinv, int n, int64_t batch, int dtype, double thr,
+                                 int64_t* n_correct, int64_t* n_incorrect, double* max_abs_dev) {
+    if (n < 1 || n > 1024) return fail(LUB_ERR_BAD_N, "n out of range");
+    if (dtype != LUB_DTYPE_F32 && dtype != LUB_DTYPE_F64) return fail(LUB_ERR_BAD_DTYPE, "dtype must be 0 or 1");
+    if (batch < 0 || (!dA && batch) || (!dAinv && batch)) return fail(LUB_ERR_BAD_ARG, "bad buffers");
+    struct Acc { unsigned long long good; unsigned int worst; unsigned int nan; };
+    Acc* d = nullptr;
+    CU(cudaMalloc((void**)&d, sizeof(Acc)));
+    CU(cudaMemsetAsync(d, 0, sizeof(Acc), g_stream));
+    if (batch > 0) {
+        const int threads = 256;
+        const long long want = (batch * 32 + threads - 1) / threads;
+        const unsigned blocks = (unsigned)std::min<long long>(want, 148ll * 16);
+        if (dtype == LUB_DTYPE_F32)
+            verify_kernel<float><<<blocks, threads, 0, g_stream>>>(static_cast<const float*>(dA), static_cast<const float*>(dAinv), n, batch, (float)thr, &d->good, &d->worst, &d->nan);
+        else
+            verify_kernel<double><<<blocks, threads, 0, g_stream>>>(static_cast<const double*>(dA), static_cast<const double*>(dAinv), n, batch, thr, &d->good, &d->worst, &d->nan);
+        CU(cudaGetLastError());
+    }
+    Acc h{};
+    CU(cudaMemcpyAsync(&h, d, sizeof(Acc), cudaMemcpyDeviceToHost, g_stream));
+    CU(cudaStreamSynchronize(g_stream));
+    cudaFree(d);
+    if (n_correct) *n_correct = (int64_t)h.good;
+    if (n_incorrect) *n_incorrect = batch - (int64_t)h.good;
+    if (max_abs_dev) { float w; memcpy(&w, &h.worst, 4); *max_abs_dev = h.nan ? NAN : (double)w; }
+    return LUB_OK;
+}
+
+int lu_batched_read_tokens(const char* path, void* out, int64_t count, int dtype) {
+    if (!path || (!out && count) || count < 0) return fail(LUB_ERR_BAD_ARG, "bad arguments");
+    if (dtype != LUB_DTYPE_F32 && dtype != LUB_DTYPE_F64) return fail(LUB_ERR_BAD_DTYPE, "dtype must be 0 or 1");
+    std::ifstream f(path);
+    if (!f) return fail(LUB_ERR_IO, std::string("cannot open ") + path);
+    // same extraction the reference uses: `file >> templateMatrix[i]` (templated/luBatchedInplace.cu:33)
+    for (int64_t i = 0; i < count; ++i) {
+        if (dtype == LUB_DTYPE_F32) f >> static_cast<float*>(out)[i];
+        else f >> static_cast<double*>(out)[i];
+        if (!f) return fail(LUB_ERR_IO, std::string(path) + ": fewer tokens than requested");
+    }
+    return LUB_OK;
+}
+
+int lu_batched_replicate(const void* tmpl, void* dst, int n, int64_t batch, int dtype) {
+    if (n < 1 || batch < 0 || !tmpl || (!dst && batch)) return fail(LUB_ERR_BAD_ARG, "bad arguments");
+    if (dtype != LUB_DTYPE_F32 && dtype != LUB_DTYPE_F64) return fail(LUB_ERR_BAD_DTYPE, "dtype must be 0 or 1");
+    const size_t mb = (size_t)n * n * esize(dtype);
+#pragma omp parallel for schedule(static)
+    for (int64_t b = 0; b < batch; ++b) memcpy(static_cast<char*>(dst) + (size_t)b * mb, tmpl, mb);
+    return LUB_OK;
+}
+
+int lu_batched_device_info(int* sm_count, int* max_smem_optin, int* clock_khz, int* cc_major, int* cc_minor) {
+    int dev = 0;
+    CU(cudaGetDevice(&dev));
+    int v = 0;
+    if (sm_count) { CU(cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev)); *sm_count = v; }
+    if (max_smem_optin) { CU(cudaDeviceGetAttribute(&v, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev)); *max_smem_optin = v; }
+    if (clock_khz) { CU(cudaDeviceGetAttribute(&v, cudaDevAttrClockRate, dev)); *clock_khz = v; }
+    if (cc_major) { CU(cudaDeviceGetAttribute(&v, cudaDevAttrComputeCapabilityMajor, dev)); *cc_major = v; }
+    if (cc_minor) { CU(cudaDeviceGetAttribute(&v, cudaDevAttrComputeCapabilityMinor, dev)); *cc_minor = v; }
+    return LUB_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,150 @@
+"""CPU tests of the boundary: the C-ABI library loads and exports every symbol that
+include/*.h declares, argument checking, fail-loudly behaviour without a GPU, and the host
+steps of main() (text input, replicate, verify.hpp-compatible check).  No compute call
+that needs a GPU is expected to succeed here."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+import matrixinversion_b200 as lub
+from conftest import ROOT, synthetic, template
+from matrixinversion_b200 import _lib
+from oracle import oracle as O
+
+try:
+    import torch
+    HAVE_CUDA = torch.cuda.is_available()
+except Exception:  # pragma: no cover
+    HAVE_CUDA = False
+
+
+def _declared(header):
+    src = open(os.path.join(ROOT, "include", header)).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(lu_batched_\w+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol():
+    names = _declared("lubatched.h")
+    assert len(names) >= 16
+    L = ctypes.CDLL(_lib.LIB_PATH)
+    for nme in names:
+        assert hasattr(L, nme), nme
+    assert sorted(_lib.SIGNATURES) == names          # the ctypes table mirrors the header
+    C = ctypes.CDLL(_lib.CUBLAS_LIB_PATH)
+    for nme in _declared("lubatched_cublas.h"):
+        assert hasattr(C, nme), nme
+    assert b"sm_100a" in _lib.lib().lu_batched_version()
+
+
+def test_product_never_links_the_oracle():
+    """The oracle is test infrastructure: nothing under matrixinversion_b200/ may mention it."""
+    pkg = os.path.join(ROOT, "matrixinversion_b200")
+    for dirpath, _, files in os.walk(pkg):
+        if os.path.basename(dirpath) == "build":
+            continue
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp")) or f == "Makefile":
+                text = open(os.path.join(dirpath, f), errors="ignore").read()
+                assert "oracle" not in text.lower().replace("test-only oracle", ""), os.path.join(dirpath, f)
+
+
+def test_argument_errors_are_codes_not_exits():
+    L = _lib.lib()
+    assert L.lu_batched_inplace(None, None, 0, 1, 0, 0) == -1     # n out of range
+    assert L.lu_batched_inplace(None, None, 33, 1, 0, 0) == -1
+    assert L.lu_batched_inplace(None, None, 4, 1, 3, 0) == -2     # mode
+    assert L.lu_batched_inplace(None, None, 4, 1, 0, 2) == -3     # dtype
+    assert L.lu_batched_inplace(None, None, 4, -1, 0, 0) == -4    # batch
+    assert b"batch" in L.lu_batched_last_error()
+    assert L.lu_batched_set_threads(48) == -4 and L.lu_batched_set_threads(512) == -4
+    assert L.lu_batched_set_threads(64) == 0 and L.lu_batched_get_threads(8, 0) == 64
+    assert L.lu_batched_set_threads(0) == 0
+    with pytest.raises(lub.LubError):
+        lub.lu_batched_inplace(np.zeros((2, 3, 4), np.float32))
+    with pytest.raises(lub.LubError):
+        lub.lu_batched_inplace(np.zeros((2, 3, 3), np.int32))
+    with pytest.raises(lub.LubError):
+        lub.lu_batched_inplace(np.zeros((2, 3, 3), np.float32), pivot_mode="lapack")
+
+
+@pytest.mark.skipif(HAVE_CUDA, reason="box has a GPU")
+def test_no_gpu_means_loud_failure_not_cpu_fallback():
+    """There is no CPU implementation of the path in the product: every compute entry
+    point must fail when no device is present."""
+    A = synthetic(4, 3, np.float32, dominant=True)
+    before = A.copy()
+    with pytest.raises(lub.LubError) as e:
+        lub.lu_batched_inplace(A, pivot_mode="none")
+    assert e.value.code in (-5, -6)
+    assert np.array_equal(A, before)
+    with pytest.raises(lub.LubError):
+        lub.geometry(8, 1000)
+
+
+def test_read_template_is_a_stream_prefix(tmp_path, inputs):
+    """first N*N tokens, not the top-left block; tokens parse like `file >> T`."""
+    toks = inputs["mtrand32_new1_f64"]
+    path = tmp_path / "mtrand32_new1.txt"
+    with open(path, "w") as f:
+        for r in range(32):
+            f.write(" ".join(repr(float(v)) for v in toks[r * 32:(r + 1) * 32]) + " \n")
+    for n in (1, 5, 18, 32):
+        A = lub.read_template(path, n, np.float32)
+        assert np.array_equal(A, template(inputs, "mtrand32_new1", n))
+        if n not in (1, 32):
+            assert not np.array_equal(A, toks.reshape(32, 32)[:n, :n].astype(np.float32))
+        assert np.array_equal(lub.read_template(path, n, np.float64), template(inputs, "mtrand32_new1", n, np.float64))
+    # numpy-style %.18e file without trailing newline (matrix.txt)
+    path2 = tmp_path / "matrix.txt"
+    with open(path2, "w") as f:
+        f.write("\n".join(" ".join("%.18e" % v for v in inputs["matrix_f64"][r * 100:(r + 1) * 100]) for r in range(100)))
+    assert np.array_equal(lub.read_template(path2, 20, np.float64), template(inputs, "matrix", 20, np.float64))
+    with pytest.raises(lub.LubError) as e:
+        lub.read_template(tmp_path / "missing.txt", 4)
+    assert e.value.code == -7
+    with pytest.raises(lub.LubError):
+        lub.read_template(path, 33)  # 1089 tokens wanted, 1024 present
+
+
+def test_replicate(inputs):
+    T = template(inputs, "mtrand32", 7)
+    A = lub.replicate(T, 11)
+    assert A.shape == (11, 7, 7) and all(np.array_equal(A[i], T) for i in range(11))
+    assert lub.replicate(T, 0).shape == (0, 7, 7)
+
+
+def test_host_verify_inv_equals_oracle_and_golden(inputs, golden):
+    for name in ("mtrand32", "mtrand32_new1"):
+        for n in (1, 16, 22, 29, 32):
+            A = template(inputs, name, n)
+            for mode in (0, 1, 2):
+                X = golden["orc_inv/%s/%d/%d" % (name, mode, n)]
+                ok, bad, dev = lub.verify_inv(A[None], X[None])
+                assert [ok, bad] == golden["ref_verify/%s/%d/%d" % (name, mode, n)].tolist()
+                assert dev == pytest.approx(O.verify_inv(A[None], X[None])[2], rel=1e-5, abs=1e-7, nan_ok=True)
+    A = synthetic(9, 40, np.float64, dominant=True)
+    X, _ = O.lu_batched(A, 0)
+    X[3] += 0.01
+    X[17, 0, 0] = np.nan
+    assert lub.verify_inv(A, X)[:2] == (38, 2) == O.verify_inv(A, X)[:2]
+
+
+def test_default_num_threads_table():
+    """templated/run.py:201-223."""
+    table = {1: 32, 2: 32, 3: 30, 4: 32, 5: 30, 6: 30, 7: 28, 8: 32, 9: 27, 10: 30, 11: 22, 12: 24, 13: 26,
+             14: 28, 15: 30, 16: 32, 17: 17, 20: 20, 31: 31, 32: 32}
+    for n, t in table.items():
+        assert lub.default_num_threads(n) == t
+
+
+def test_shard_range_partitions_the_batch():
+    for batch in (0, 1, 7, 8, 1000, 1_000_000):
+        for world in (1, 2, 3, 4, 8):
+            spans = [lub.shard_range(batch, r, world) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == batch
+            assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+            assert max(hi - lo for lo, hi in spans) <= -(-batch // world)

@@ -1,0 +1,258 @@
+"""GPU parity tests (run with `-m gpu` on the B200 box).  Everything goes through the C ABI
+(ctypes -> liblubatched.so); the CPU oracle and the reference's own kernels rebuilt for
+sm_100 (oracle/_ref, built in the container from /root/reference) are the checkers.
+
+Tolerances (north star):
+  * pivots / permutation vectors: bit-exact;
+  * inverses: ||A X - I||_F <= C_RES * N * eps * kappa_2(A)   (residual in fp64, kappa from
+    numpy in fp64 -- never the reference's calc_cond_num), and elementwise
+    max|X - X_ref| <= C_ELEM * N * eps * kappa_2(A) * max|X_ref| against the oracle and
+    against the reference GPU kernels.
+"""
+import io
+
+import numpy as np
+import pytest
+
+import matrixinversion_b200 as lub
+from conftest import FILES, synthetic, template
+from oracle import oracle as O
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+C_RES = 128.0    # the "stated constant c": oracle worst case is 36, Gauss-Jordan about 2x that
+C_ELEM = 16.0
+EPS = {np.dtype(np.float32): 2.0 ** -23, np.dtype(np.float64): 2.0 ** -52}
+MODES = (0, 1, 2)
+
+
+def gpu_invert(A, mode, want_piv=True):
+    """numpy [b, n, n] -> (inverse, piv) through the device-pointer C ABI."""
+    dA = torch.from_numpy(np.ascontiguousarray(A)).cuda()
+    piv = torch.full((A.shape[0], A.shape[1]), -7, dtype=torch.int32, device="cuda") if want_piv else None
+    lub.lu_batched_inplace(dA, piv, mode)
+    torch.cuda.synchronize()
+    return dA.cpu().numpy(), (piv.cpu().numpy() if want_piv else None)
+
+
+def check_values(A, X, Xref, what):
+    """Residual + elementwise bounds for every matrix of a (small) batch."""
+    eps = EPS[A.dtype]
+    n = A.shape[1]
+    A64 = A.astype(np.float64)
+    kappa = np.linalg.cond(A64)
+    res = np.linalg.norm(A64 @ X.astype(np.float64) - np.eye(n), axis=(1, 2))
+    bound = C_RES * n * eps * kappa
+    assert np.all(res <= bound), (what, float((res / bound).max()))
+    if Xref is not None:
+        scale = np.abs(Xref).max(axis=(1, 2))
+        diff = np.abs(X.astype(np.float64) - Xref.astype(np.float64)).max(axis=(1, 2))
+        ebound = C_ELEM * n * eps * kappa * scale
+        assert np.all(diff <= ebound), (what, float((diff / ebound).max()))
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_reference_inputs_every_n_every_mode(inputs, dtype):
+    """The reference's own input files, N = 1..32, replicated as main() does (Q6): pivots
+    bit-exact vs the oracle, inverse within tolerance of it, every replica identical."""
+    B = 37  # not a multiple of any matrices-per-warp count: exercises the tail tile
+    for name in FILES:
+        values_ok = name != "mtrand32_new"  # 0..9 integers: singular prefixes exist -> pivots only
+        for n in range(1, 33):
+            T = template(inputs, name, n, dtype)
+            A = lub.replicate(T, B)
+            for mode in MODES:
+                X, piv = gpu_invert(A, mode)
+                with np.errstate(all="ignore"):
+                    Xo, po = O.lu_batched(T[None], mode)
+                assert np.array_equal(piv, np.repeat(po, B, axis=0)), (name, n, mode)
+                assert all(np.array_equal(X[0], X[i], equal_nan=True) for i in range(1, B)), (name, n, mode)
+                if values_ok and np.isfinite(Xo).all() and np.linalg.cond(T.astype(np.float64)) < 0.01 / EPS[np.dtype(dtype)]:
+                    check_values(T[None], X[:1], Xo, (name, n, mode))
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_distinct_random_matrices(dtype):
+    """SURVEY.md 8(d) extra set (i): distinct uniform(0,1) matrices -- different pivot
+    sequences inside one warp."""
+    for n in range(1, 33):
+        A = synthetic(n, 203, dtype)
+        for mode in MODES:
+            X, piv = gpu_invert(A, mode)
+            with np.errstate(all="ignore"):
+                Xo, po = O.lu_batched(A, mode)
+            assert np.array_equal(piv, po), (n, mode)
+            good = np.isfinite(Xo).all(axis=(1, 2)) & (np.linalg.cond(A.astype(np.float64)) < 0.001 / EPS[np.dtype(dtype)])
+            check_values(A[good], X[good], Xo[good], (n, mode))
+
+
+def test_tie_heavy_integer_matrices_pivots_exact():
+    """Small-integer entries: many exact ties and zeros in every column, singular matrices
+    included (values may be inf/NaN as in the reference, Q7) -- the permutation must still
+    match find_pivot / find_pivot_parallel bit for bit."""
+    rng = np.random.default_rng(42)
+    for n in range(1, 33):
+        for dtype in (np.float32, np.float64):
+            A = rng.integers(-3, 4, size=(67, n, n)).astype(dtype)
+            for mode in (1, 2):
+                _, piv = gpu_invert(A, mode)
+                _, po = O.lu_batched(A, mode, lu_only=True)
+                assert np.array_equal(piv, po), (n, mode, dtype)
+
+
+@pytest.mark.skipif(not O.have_ref("ref_parallel_piv_f32"), reason="oracle/_ref not built")
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_against_reference_gpu_kernels(inputs, dtype):
+    """The reference's kernels rebuilt for sm_100 (unmodified for values; build_ref.sh's
+    one-store patch for the permutation vector) on identical inputs."""
+    for name in ("mtrand32", "mtrand32_new1"):
+        for n in (1, 2, 3, 4, 7, 8, 13, 16, 17, 18, 20, 24, 27, 31, 32):
+            T = template(inputs, name, n, dtype)
+            A = np.concatenate([lub.replicate(T, 5), synthetic(n, 59, dtype)])
+            for mode in MODES:
+                X, piv = gpu_invert(A, mode)
+                Xr, _, _ = O.ref_gpu_invert(A, mode)
+                if mode:
+                    Xp, pr, _ = O.ref_gpu_invert(A, mode, want_piv=True)
+                    assert np.array_equal(Xp, Xr, equal_nan=True)       # the patch changes no arithmetic
+                    assert np.array_equal(piv, pr), (name, n, mode)     # bit-exact pivots vs the reference
+                good = np.isfinite(Xr).all(axis=(1, 2)) & (np.linalg.cond(A.astype(np.float64)) < 0.001 / EPS[np.dtype(dtype)])
+                check_values(A[good], X[good], Xr[good], (name, n, mode))
+
+
+def test_edge_cases():
+    # empty batch: a no-op
+    z = torch.empty((0, 5, 5), device="cuda")
+    lub.lu_batched_inplace(z, None, "parallel")
+    # batch = 1, piv = None, N = 1
+    X, _ = gpu_invert(np.full((1, 1, 1), 4.0, np.float32), 2, want_piv=False)
+    assert X[0, 0, 0] == pytest.approx(0.25)
+    # pointer aligned to the element but not to 16 bytes (odd N, view starting at matrix 1)
+    for n, dtype in ((5, np.float32), (31, np.float32), (7, np.float64), (19, np.float32)):
+        A = synthetic(n, 41, dtype)
+        base = torch.from_numpy(A).cuda()
+        view = base[1:]
+        assert view.data_ptr() % 16 != 0 or n * n * A.itemsize % 16 == 0
+        piv = torch.zeros((40, n), dtype=torch.int32, device="cuda")
+        lub.lu_batched_inplace(view, piv, "parallel")
+        Xfull, pfull = gpu_invert(A[1:], 2)
+        assert np.array_equal(view.cpu().numpy(), Xfull) and np.array_equal(piv.cpu().numpy(), pfull)
+        assert np.array_equal(base[0].cpu().numpy(), A[0])  # neighbour untouched
+    # singular input: inf/NaN, no status, no crash (Q7)
+    X, piv = gpu_invert(np.zeros((3, 6, 6), np.float32), 1)
+    assert not np.isfinite(X).any() and np.array_equal(piv, np.tile(np.arange(6, dtype=np.int32), (3, 1)))
+    # mode none writes the identity permutation
+    _, piv = gpu_invert(synthetic(9, 10, np.float32, dominant=True), 0)
+    assert np.array_equal(piv, np.tile(np.arange(9, dtype=np.int32), (10, 1)))
+    # errors are exceptions, not exits
+    with pytest.raises(lub.LubError):
+        lub.lu_batched_inplace(torch.zeros((2, 33, 33), device="cuda"))
+    with pytest.raises(lub.LubError):
+        lub.lu_batched_inplace(torch.zeros((2, 4, 4)))  # CPU tensor
+
+
+def test_numthreads_knob_and_host_pipeline_are_bitwise_equivalent():
+    for n, dtype in ((6, np.float32), (18, np.float32), (32, np.float32), (12, np.float64), (32, np.float64)):
+        A = synthetic(n, 1001, dtype)
+        X0, p0 = gpu_invert(A, 2)
+        for t in (32, 64, 256):
+            lub.set_num_threads(t)
+            try:
+                X, p = gpu_invert(A, 2)
+            finally:
+                lub.set_num_threads(0)
+            assert np.array_equal(X, X0, equal_nan=True) and np.array_equal(p, p0), (n, t)
+        H = A.copy()
+        hp = np.zeros((1001, n), np.int32)
+        lub.lu_batched_inplace(H, hp, "parallel")   # numpy -> chunked H2D / kernel / D2H pipeline
+        assert np.array_equal(H, X0, equal_nan=True) and np.array_equal(hp, p0)
+
+
+def test_device_verify_equals_host_verify():
+    A = synthetic(16, 500, np.float32, dominant=True)
+    X, _ = gpu_invert(A, 0)
+    X[5] *= 1.01
+    X[77, 3, 3] = np.nan
+    host = lub.verify_inv(A, X)
+    dev = lub.verify_inv(torch.from_numpy(A).cuda(), torch.from_numpy(X).cuda())
+    assert host[:2] == dev[:2] == (498, 2) == O.verify_inv(A, X)[:2]
+    assert np.isnan(host[2]) and np.isnan(dev[2])
+
+
+def test_run_main_prints_the_reference_stdout_contract(inputs):
+    buf = io.StringIO()
+    res = lub.run_main(32, 1000, pivot_mode="none", template=template(inputs, "mtrand32", 32), out=buf)
+    lines = buf.getvalue().splitlines()
+    want = ["Matrix size:", "Number of matrices:", "Number of threads per block:", "Threads per matrix:",
+            "Matrices per block:", "Number of blocks:", "Reading data from file.", "Condition number of the matrix is:",
+            "Time taken to read data:", "Data read from file.", "Data copied to device.", "Kernel execution time:",
+            "Data copied back to host.", "Correct inversions:", "Incorrect inversions:", "Time taken to verify inverse:"]
+    assert len(lines) == len(want) and all(l.startswith(w) for l, w in zip(lines, want)), lines
+    # BASELINE config 1: N=32, B=1000, fp32, no pivoting, mtrand32.txt -> 1000 correct
+    assert res["correct"] == 1000 and res["incorrect"] == 0 and res["kernel_ms"] > 0
+
+
+# ---- BASELINE.json full-size configurations: size-independent properties ---------------------
+
+def _full_size(n, batch, dtype, mode, tmpl):
+    tdtype = torch.float32 if dtype == np.float32 else torch.float64
+    # (a) the reference's convention: one template replicated -> every inverse identical,
+    #     and identical to a small-batch run already checked against the oracle
+    dT = torch.from_numpy(tmpl).cuda()
+    dA = dT.unsqueeze(0).expand(batch, n, n).contiguous()
+    piv = torch.empty((batch, n), dtype=torch.int32, device="cuda")
+    lub.lu_batched_inplace(dA, piv, mode)
+    Xs, ps = gpu_invert(tmpl[None], mode)
+    assert bool((dA == torch.from_numpy(Xs).cuda()).all()) and bool((piv == torch.from_numpy(ps).cuda()).all())
+    ok, bad, _ = lub.verify_inv(dT.unsqueeze(0).expand(batch, n, n).contiguous(), dA)
+    assert (ok, bad) == (batch, 0)
+    del dA
+    # (b) distinct diagonally-dominant matrices: verifyInv passes everywhere, inv(inv(A)) ~ A,
+    #     pivots of a 10k sample equal the oracle's
+    g = torch.Generator(device="cuda").manual_seed(1000 * n + batch % 997)
+    dA = torch.rand((batch, n, n), generator=g, device="cuda", dtype=tdtype)
+    dA += n * torch.eye(n, device="cuda", dtype=tdtype)
+    orig = dA.clone()
+    lub.lu_batched_inplace(dA, piv, mode)
+    ok, bad, dev = lub.verify_inv(orig, dA)
+    assert (ok, bad) == (batch, 0) and dev < 1e-4
+    sample = slice(batch // 2 - 5000, batch // 2 + 5000)
+    _, po = O.lu_batched(orig[sample].cpu().numpy(), mode, lu_only=True)
+    assert np.array_equal(piv[sample].cpu().numpy(), po)
+    lub.lu_batched_inplace(dA, None, mode)
+    rel = ((dA - orig).abs().amax(dim=(1, 2)) / orig.abs().amax(dim=(1, 2))).max().item()
+    assert rel < (1e-4 if dtype == np.float32 else 1e-12)
+
+
+def test_config2_n20_1M_fp32_nopivot(inputs):
+    _full_size(20, 1_000_000, np.float32, 0, template(inputs, "mtrand32_new1", 20))
+
+
+def test_config3_n18_1M_fp32_parallel(inputs):
+    _full_size(18, 1_000_000, np.float32, 2, template(inputs, "mtrand32_new1", 18))
+
+
+def test_headline_n32_1M_fp32_parallel(inputs):
+    _full_size(32, 1_000_000, np.float32, 2, template(inputs, "mtrand32_new1", 32))
+
+
+def test_config5_n32_1M_fp64_pivot(inputs):
+    _full_size(32, 1_000_000, np.float64, 2, template(inputs, "mtrand64", 32, np.float64))
+
+
+def test_cublas_baseline_agrees():
+    """The comparison baseline computes the same inverses (row-major in, row-major out)."""
+    import ctypes
+    from matrixinversion_b200 import _lib
+    C = _lib.cublas_lib()
+    for n, dtype in ((8, np.float32), (20, np.float32), (32, np.float64)):
+        A = synthetic(n, 300, dtype, dominant=True)
+        dA = torch.from_numpy(A).cuda()
+        dX = torch.empty_like(dA)
+        t1, t2 = ctypes.c_float(), ctypes.c_float()
+        rc = C.lu_batched_cublas_baseline(dA.data_ptr(), dX.data_ptr(), n, 300, 0 if dtype == np.float32 else 1, 1,
+                                          ctypes.byref(t1), ctypes.byref(t2))
+        assert rc == 0
+        X, _ = gpu_invert(A, 2)
+        assert np.allclose(dX.cpu().numpy(), X, rtol=0, atol=(1e-5 if dtype == np.float32 else 1e-13))
