@@ -1,0 +1,492 @@
+// lub_fast.cuh -- second-generation hot-path kernel (same result as lub_kernel.cuh, see the
+// algorithm notes there) built around what Nsight Compute showed on B200 for the first one:
+// the LSU / shared-memory pipe, not HBM or the FMA pipe, was the limiter (74 % busy, 63 % of
+// its wavefronts bank-conflict replays; profiles/r01_v1_n32_f32_parallel.md).
+//
+//   * the shared-memory image of a tile keeps 16-byte vector access but pads every row (and
+//     every matrix) by a few words, chosen at compile time so that a column walk (pivot
+//     search) and the 2-D register load no longer map rows onto the same banks;
+//   * per-step pivot row / multiplier exchange goes through two small double-buffered
+//     shared-memory vectors written by the owning lanes with 128-bit stores and read back
+//     with 128-bit broadcast loads (about 10 LSU instructions per step per tile instead of
+//     21 shuffles), one __syncwarp per step, no block barrier anywhere;
+//   * pivot pre-pass for N > 16 runs one matrix per warp with lane = row position:
+//     column value -> REDUX max -> ballot -> first set bit, one shuffle to swap two lanes'
+//     row ids.  find_pivot_parallel's tree (parallel_pivot/luBatchedInplace.cuh:12-44) is
+//     reproduced by a per-step compile-time mask of the slots the tree can reach plus a
+//     rank tie-break executed only when two candidates hold the same maximal value;
+//   * multipliers are produced by the lanes owning column k directly into consecutive
+//     registers (no gather moves), and FFMA2 takes them as a scalar-broadcast operand.
+#pragma once
+#include "lub_kernel.cuh"
+
+namespace lub {
+
+constexpr int cdiv_(int a, int b) { return (a + b - 1) / b; }
+constexpr int gcd_(int a, int b) { return b == 0 ? a : gcd_(b, a % b); }
+constexpr int roundup_(int a, int b) { return cdiv_(a, b) * b; }
+
+// conflict degree of `rows` lanes walking one column of an image whose rows are `pw`
+// 32-bit words apart, elements `ew` words wide
+constexpr int column_conflict(int rows, int pw, int ew) {
+    const int slots = 32 / ew;
+    const int distinct = slots / gcd_((pw / ew) % slots == 0 ? slots : (pw / ew) % slots, slots);
+    return cdiv_(rows, distinct);
+}
+
+template <typename T, int N>
+constexpr int pick_row_pad() {  // elements; multiple of 16 bytes
+    constexpr int ES = sizeof(T), EPV = 16 / ES, EW = ES / 4;
+    int best = 0, best_deg = 1 << 30;
+    for (int pad = 0; pad <= 3 * EPV; pad += EPV) {
+        const int deg = column_conflict(N, (N + pad) * EW, EW);
+        if (deg < best_deg) { best_deg = deg; best = pad; }
+    }
+    return best;
+}
+
+template <typename T, int N, int P, int MPW>
+constexpr int pick_mat_pad() {  // elements; multiple of 16 bytes; spreads the tile's matrices over banks
+    constexpr int ES = sizeof(T), EPV = 16 / ES, EW = ES / 4;
+    if (MPW == 1) return 0;
+    for (int pad = 0; pad < 32 / EW; pad += EPV) {
+        const int msw = (N * P + pad) * EW;
+        if ((msw % 8) == 4) return pad;  // 4 * odd words: eight matrices land on eight different bank groups
+    }
+    return 0;
+}
+
+template <typename T, int N, int GR, int GC, int MODE>
+struct FastLayout {
+    static constexpr int ES = sizeof(T);
+    static constexpr int EPV = 16 / ES;
+    // widest power-of-two chunk (elements) that divides every row: vector width of all row accesses
+    static constexpr int CH = (N % EPV == 0) ? EPV : ((EPV == 4 && N % 2 == 0) ? 2 : 1);
+    static constexpr int G = GR * GC;
+    static_assert(G >= 1 && G <= 32 && (32 % G) == 0, "G must divide 32");
+    static constexpr int MPW = 32 / G;
+    static constexpr int CPR = N / CH;              // chunks per row
+    static constexpr int CPL = cdiv_(CPR, GC);      // chunks per lane (cyclic over GC)
+    static constexpr int LC = CPL * CH;
+    static constexpr int LR = cdiv_(N, GR);         // rows per lane (cyclic over GR)
+    static constexpr bool ROWVEC = (CH == EPV);     // rows are whole 16-byte chunks -> padded image
+    static constexpr int RPAD = ROWVEC ? pick_row_pad<T, N>() : 0;
+    static constexpr int P = N + RPAD;              // image row stride (elements)
+    static constexpr int MPAD = ROWVEC ? pick_mat_pad<T, N, P, MPW>() : 0;
+    static constexpr int MS = N * P + MPAD;         // image matrix stride (elements)
+    static constexpr int LRP = roundup_(LR, EPV);   // multiplier vector per lane-row, 16-byte padded
+    static constexpr int XROW = roundup_(N, EPV);
+    static constexpr int XCOL = GR * LRP;
+    static constexpr int XB = XROW + XCOL;          // one exchange buffer (elements)
+    static constexpr int IMG_BYTES = roundup_(MPW * MS * ES, 16) + 16;
+    static constexpr int PERM_BYTES = (MODE != kModeNone) ? roundup_(MPW * N * 4, 16) : 0;
+    static constexpr int XBUF_BYTES = (G > 1) ? MPW * 2 * XB * ES : 0;
+    static constexpr int WARP_BYTES = IMG_BYTES + PERM_BYTES + XBUF_BYTES;
+    static constexpr int HEADER_BYTES = 64;
+    // 16-byte units, for the padded copy
+    static constexpr int CPR16 = N * ES / 16, RPAD16 = RPAD * ES / 16, MPAD16 = MPAD * ES / 16;
+};
+
+// Lane-dependent selects are written as PTX selp so that the compiler keeps them as one
+// FSEL each: given a C++ ?: it if-converts the whole rank-1 update into two divergent copies
+// (one per value of "this lane owns column k"), doubling the FMA work of every warp.
+__device__ __forceinline__ float sel_t(bool p, float x, float y) {
+    float d;
+    asm("{ .reg .pred q; setp.ne.s32 q, %3, 0; selp.f32 %0, %1, %2, q; }" : "=f"(d) : "f"(x), "f"(y), "r"((int)p));
+    return d;
+}
+__device__ __forceinline__ double sel_t(bool p, double x, double y) {
+    double d;
+    asm("{ .reg .pred q; setp.ne.s32 q, %3, 0; selp.f64 %0, %1, %2, q; }" : "=d"(d) : "d"(x), "d"(y), "r"((int)p));
+    return d;
+}
+
+// In-place predicated overwrite: `if (p) x = v` as ONE predicated move on x's own register.
+// (A select creates a new value; when x is half of an FFMA2 register pair the compiler then has
+// to rebuild the pair with an extra MOV per row per step.)
+__device__ __forceinline__ void set_if(bool p, float& x, float v) {
+    asm("{ .reg .pred q; setp.ne.s32 q, %1, 0; @q mov.f32 %0, %2; }" : "+f"(x) : "r"((int)p), "f"(v));
+}
+__device__ __forceinline__ void set_if(bool p, double& x, double v) {
+    asm("{ .reg .pred q; setp.ne.s32 q, %1, 0; @q mov.f64 %0, %2; }" : "+d"(x) : "r"((int)p), "d"(v));
+}
+
+// ---- vector helpers -------------------------------------------------------------------------
+
+template <typename T, int CH> struct Vec;
+template <> struct Vec<float, 4> { using V = float4; };
+template <> struct Vec<float, 2> { using V = float2; };
+template <> struct Vec<float, 1> { using V = float; };
+template <> struct Vec<double, 2> { using V = double2; };
+template <> struct Vec<double, 1> { using V = double; };
+
+template <typename T, int CH>
+__device__ __forceinline__ void ld_vec(const T* __restrict__ p, T* __restrict__ dst) {
+    using V = typename Vec<T, CH>::V;
+    const V v = *reinterpret_cast<const V*>(p);
+    const T* e = reinterpret_cast<const T*>(&v);
+#pragma unroll
+    for (int i = 0; i < CH; ++i) dst[i] = e[i];
+}
+template <typename T, int CH>
+__device__ __forceinline__ void st_vec(T* __restrict__ p, const T* __restrict__ src) {
+    using V = typename Vec<T, CH>::V;
+    V v;
+    T* e = reinterpret_cast<T*>(&v);
+#pragma unroll
+    for (int i = 0; i < CH; ++i) e[i] = src[i];
+    *reinterpret_cast<V*>(p) = v;
+}
+
+// ---- padded copy global <-> image (ROWVEC) ---------------------------------------------------
+
+template <typename T, typename L, int N>
+__device__ __forceinline__ void copy_in_padded(unsigned char* __restrict__ img, const T* __restrict__ src,
+                                               int nchunks, int lane) {
+    const uint4* s = reinterpret_cast<const uint4*>(src);
+    uint4* d = reinterpret_cast<uint4*>(img);
+    auto dst_of = [](int q) {
+        const int rowidx = q / L::CPR16;
+        int o = q + rowidx * L::RPAD16;
+        if (L::MPAD16 != 0) o += (rowidx / N) * L::MPAD16;
+        return o;
+    };
+    int q = lane;
+    for (; q + 96 < nchunks; q += 128) {
+        const uint4 v0 = ld_stream16(s + q), v1 = ld_stream16(s + q + 32);
+        const uint4 v2 = ld_stream16(s + q + 64), v3 = ld_stream16(s + q + 96);
+        d[dst_of(q)] = v0;
+        d[dst_of(q + 32)] = v1;
+        d[dst_of(q + 64)] = v2;
+        d[dst_of(q + 96)] = v3;
+    }
+    for (; q < nchunks; q += 32) d[dst_of(q)] = ld_stream16(s + q);
+}
+
+template <typename T, typename L, int N>
+__device__ __forceinline__ void copy_out_padded(T* __restrict__ dst, const unsigned char* __restrict__ img,
+                                                int nchunks, int lane) {
+    uint4* d = reinterpret_cast<uint4*>(dst);
+    const uint4* s = reinterpret_cast<const uint4*>(img);
+    for (int q = lane; q < nchunks; q += 32) {
+        const int rowidx = q / L::CPR16;
+        int o = q + rowidx * L::RPAD16;
+        if (L::MPAD16 != 0) o += (rowidx / N) * L::MPAD16;
+        st_stream16(d + q, s[o]);
+    }
+}
+
+// ---- warp-wide pivot pre-pass (one matrix, lane = row position) -----------------------------
+
+constexpr unsigned reach_mask_of(int n) {  // bit t set <=> slot t of an n-slot tree reaches slot 0
+    unsigned m = 0;
+    for (int t = 0; t < n && t < 32; ++t)
+        if (tree_slot_rank(t, n) >= 0) m |= 1u << t;
+    return m;
+}
+template <int N> struct ReachMask { static constexpr unsigned value = reach_mask_of(N); };
+
+__device__ __forceinline__ uint32_t warp_max_bits(uint32_t v) { return __reduce_max_sync(0xffffffffu, v); }
+__device__ __forceinline__ unsigned long long warp_max_bits(unsigned long long v) {
+    const uint32_t hi = (uint32_t)(v >> 32), lo = (uint32_t)v;
+    const uint32_t mh = __reduce_max_sync(0xffffffffu, hi);
+    const uint32_t ml = __reduce_max_sync(0xffffffffu, hi == mh ? lo : 0u);
+    return ((unsigned long long)mh << 32) | ml;
+}
+
+// MI matrices are searched in lock step: their dependency chains (LDS -> REDUX -> VOTE -> SHFL)
+// are independent, so the scheduler overlaps them.
+template <typename T, int N, int MODE, int P, int MS, int MI>
+__device__ __forceinline__ void prepass_warp(const T* __restrict__ img0, int* __restrict__ perm0,
+                                             const int8_t* __restrict__ slot_rank, int lane) {
+    using U = typename FpBits<T>::U;
+    constexpr unsigned ALL = (N >= 32) ? 0xffffffffu : ((1u << N) - 1u);
+    constexpr unsigned REACH = ReachMask<N>::value;
+    int prow[MI];  // original row sitting at position `lane`
+#pragma unroll
+    for (int m = 0; m < MI; ++m) prow[m] = (lane < N) ? lane : 0;
+#pragma unroll
+    for (int k = 0; k < N - 1; ++k) {
+        // rows this step may pick: serial = every row below k; parallel = the slots the
+        // reference tree merges into slot 0 (slot t <-> row k+1+t), plus the seed row k
+        const unsigned vmask = ((MODE == kModeParallel) ? ((REACH << (k + 1)) | (1u << k)) : (ALL << k)) & ALL;
+        const bool valid = (vmask >> lane) & 1u;
+        U v[MI], mx[MI];
+        unsigned bal[MI];
+#pragma unroll
+        for (int m = 0; m < MI; ++m) v[m] = FpBits<T>::absbits(img0[m * MS + prow[m] * P + k]);
+#pragma unroll
+        for (int m = 0; m < MI; ++m) mx[m] = warp_max_bits(valid ? v[m] : U(0));
+#pragma unroll
+        for (int m = 0; m < MI; ++m) bal[m] = __ballot_sync(0xffffffffu, valid && v[m] == mx[m]);
+#pragma unroll
+        for (int m = 0; m < MI; ++m) {
+            int wl;
+            if (MODE == kModeSerial) {
+                wl = __ffs(bal[m]) - 1;  // lowest row among the maxima; row k itself if it ties (strict '>')
+            } else {
+                if (bal[m] & (1u << k)) {
+                    wl = k;  // nothing strictly larger than |A[k][k]|
+                } else if ((bal[m] & (bal[m] - 1u)) == 0u) {
+                    wl = __ffs(bal[m]) - 1;
+                } else {  // equal maxima in several slots: the tree keeps the lowest rank
+                    const bool cand = (bal[m] >> lane) & 1u;
+                    const unsigned rk = cand ? (unsigned)slot_rank[cand ? lane - k - 1 : 0] : 0xffu;
+                    const unsigned best = __reduce_min_sync(0xffffffffu, rk);
+                    wl = __ffs(__ballot_sync(0xffffffffu, rk == best)) - 1;
+                }
+            }
+            // swap the row ids of positions k and wl (a no-op when wl == k)
+            const int other = __shfl_sync(0xffffffffu, prow[m], lane == k ? wl : k);
+            prow[m] = (lane == k || lane == wl) ? other : prow[m];
+        }
+    }
+#pragma unroll
+    for (int m = 0; m < MI; ++m)
+        if (lane < N) perm0[m * N + lane] = prow[m];
+}
+
+// generic sub-warp pre-pass on a strided image (N <= 16): see pivot_prepass in lub_kernel.cuh
+template <typename T, int N, int G, int MODE, int P>
+__device__ __forceinline__ void prepass_group(const T* __restrict__ mimg, int* __restrict__ perm,
+                                              const int8_t* __restrict__ slot_rank, int g) {
+    using U = typename FpBits<T>::U;
+    for (int i = g; i < N; i += G) perm[i] = i;
+    __syncwarp();
+    for (int k = 0; k < N - 1; ++k) {
+        U best_v = FpBits<T>::absbits(mimg[perm[k] * P + k]);
+        unsigned best_p = 0;
+        for (int t = g; t < N - 1 - k; t += G) {
+            int pr;
+            if (MODE == kModeParallel) {
+                pr = slot_rank[t];
+                if (pr < 0) continue;
+            } else {
+                pr = t;
+            }
+            const U v = FpBits<T>::absbits(mimg[perm[k + 1 + t] * P + k]);
+            const unsigned p = ((unsigned)(pr + 1) << 8) | (unsigned)(t + 1);
+            if (v > best_v || (v == best_v && p < best_p)) { best_v = v; best_p = p; }
+        }
+#pragma unroll
+        for (int off = G / 2; off > 0; off >>= 1) {
+            const U ov = __shfl_xor_sync(0xffffffffu, best_v, off);
+            const unsigned op = __shfl_xor_sync(0xffffffffu, best_p, off);
+            if (ov > best_v || (ov == best_v && op < best_p)) { best_v = ov; best_p = op; }
+        }
+        __syncwarp();
+        if (g == 0 && best_p != 0) {
+            const int p = k + (int)(best_p & 0xffu);
+            const int tmp = perm[k];
+            perm[k] = perm[p];
+            perm[p] = tmp;
+        }
+        __syncwarp();
+    }
+}
+
+// ---- the kernel -------------------------------------------------------------------------------
+
+template <typename T, int N, int GR, int GC, int MODE, int MINB = 1>
+__global__ void __launch_bounds__(kMaxThreads, MINB)
+lub_fast_kernel(T* __restrict__ A, int32_t* __restrict__ piv, long long batch) {
+    using L = FastLayout<T, N, GR, GC, MODE>;
+    constexpr int G = L::G, MPW = L::MPW, LR = L::LR, LC = L::LC, CH = L::CH, CPL = L::CPL, CPR = L::CPR;
+    constexpr int P = L::P, MS = L::MS, EPV = L::EPV, LRP = L::LRP;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    const int nwarps = blockDim.x >> 5;
+    int8_t* slot_rank = reinterpret_cast<int8_t*>(smem_raw);
+    unsigned char* wbase = smem_raw + L::HEADER_BYTES + (size_t)warp * L::WARP_BYTES;
+    int* perm_all = reinterpret_cast<int*>(wbase + L::IMG_BYTES);
+    T* xbuf_all = reinterpret_cast<T*>(wbase + L::IMG_BYTES + L::PERM_BYTES);
+
+    if (MODE == kModeParallel) {
+        if (threadIdx.x < N) slot_rank[threadIdx.x] = (int8_t)tree_slot_rank(threadIdx.x, N);
+        __syncthreads();
+    }
+
+    const int g = lane % G;
+    const int ml = lane / G;
+    const int gr = g / GC;
+    const int gc = g % GC;
+    const int grp_base = ml * G;
+    T* xb0 = xbuf_all + ml * (2 * L::XB);
+
+    const long long ntiles = (batch + MPW - 1) / MPW;
+#pragma unroll 1
+    for (long long tile = (long long)blockIdx.x * nwarps + warp; tile < ntiles;
+         tile += (long long)gridDim.x * nwarps) {
+        const long long first = tile * MPW;
+        const int nm = (batch - first < MPW) ? (int)(batch - first) : MPW;
+        T* gspan = A + first * (long long)(N * N);
+        T* img;
+        if constexpr (L::ROWVEC) {
+            img = reinterpret_cast<T*>(wbase);
+            copy_in_padded<T, L, N>(wbase, gspan, nm * N * L::CPR16, lane);
+        } else {
+            const unsigned mis = (unsigned)(reinterpret_cast<uintptr_t>(gspan) & 15u);
+            img = reinterpret_cast<T*>(wbase + mis);
+            copy_in<T>(img, gspan, nm * N * N, MPW * N * N, lane);
+        }
+        __syncwarp();
+
+        T* mimg = img + ml * MS;
+        int* perm = perm_all + ml * N;
+        if (MODE != kModeNone) {
+            if (N > 16) {
+                constexpr int MI = (MPW < 4) ? MPW : 4;
+#pragma unroll 1
+                for (int m = 0; m < MPW; m += MI)
+                    prepass_warp<T, N, MODE, P, MS, MI>(img + m * MS, perm_all + m * N, slot_rank, lane);
+            } else {
+                prepass_group<T, N, G, MODE, P>(mimg, perm, slot_rank, g);
+            }
+            __syncwarp();
+        }
+
+        // ---- registers <- image: rows permuted, LR x LC block per lane ---------------------
+        T a[LR][LC];
+#pragma unroll
+        for (int li = 0; li < LR; ++li) {
+            const int i = li * GR + gr;
+            const bool rok = (li * GR + GR - 1 < N) || (i < N);
+            int prow = i;
+            if (MODE != kModeNone) prow = rok ? perm[i] : 0;
+            const T* rowp = mimg + prow * P;
+#pragma unroll
+            for (int q = 0; q < CPL; ++q) {
+                const int cq = q * GC + gc;
+                const bool ok = rok && ((q * GC + GC - 1 < CPR) || (cq < CPR));
+                if (ok) {
+                    ld_vec<T, CH>(rowp + cq * CH, &a[li][q * CH]);
+                } else {
+#pragma unroll
+                    for (int w = 0; w < CH; ++w) a[li][q * CH + w] = T(0);
+                }
+            }
+        }
+
+        // ---- Gauss-Jordan with deferred row scaling ------------------------------------------
+        T dinv[LR];
+#pragma unroll
+        for (int li = 0; li < LR; ++li) dinv[li] = T(0);
+#pragma unroll
+        for (int k = 0; k < N; ++k) {
+            const int gro = k % GR, lk = k / GR;
+            const int cj = k / CH, gco = cj % GC, ck = (cj / GC) * CH + (k % CH);
+            const bool own_row = (GR == 1) || (gr == gro);
+            const bool own_col = (GC == 1) || (gc == gco);
+            T* rowbuf = xb0 + (k & 1) * L::XB;
+            T* colbuf = rowbuf + L::XROW;
+            T r[LC], nf[LRP];
+
+            if (GR > 1) {  // owners of row k publish their pieces
+                if (own_row) {
+#pragma unroll
+                    for (int q = 0; q < CPL; ++q) {
+                        const int cq = q * GC + gc;
+                        if ((q * GC + GC - 1 < CPR) || (cq < CPR)) st_vec<T, CH>(rowbuf + cq * CH, &a[lk][q * CH]);
+                    }
+                }
+            }
+            T rinv;
+            if (GC > 1) {  // owners of column k compute the multipliers and publish them
+                const T pv = shfl_t(a[lk][ck], grp_base + gro * GC + gco);
+                rinv = rcp_t(pv);
+#pragma unroll
+                for (int li = 0; li < LRP; ++li) nf[li] = (li < LR) ? -(a[li < LR ? li : 0][ck] * rinv) : T(0);
+                nf[lk] = sel_t(own_row, T(0), nf[lk]);
+                if (own_col) {
+#pragma unroll
+                    for (int v = 0; v < LRP; v += EPV) st_vec<T, EPV>(colbuf + gr * LRP + v, &nf[v]);
+                }
+            }
+            if (G > 1) __syncwarp();
+            if (GR > 1) {
+#pragma unroll
+                for (int q = 0; q < CPL; ++q) {
+                    const int cq = q * GC + gc;
+                    if ((q * GC + GC - 1 < CPR) || (cq < CPR)) {
+                        ld_vec<T, CH>(rowbuf + cq * CH, &r[q * CH]);
+                    } else {
+#pragma unroll
+                        for (int w = 0; w < CH; ++w) r[q * CH + w] = T(0);
+                    }
+                }
+            } else {
+#pragma unroll
+                for (int lj = 0; lj < LC; ++lj) r[lj] = a[lk][lj];
+            }
+            if (GC > 1) {
+#pragma unroll
+                for (int v = 0; v < LRP; v += EPV) ld_vec<T, EPV>(colbuf + gr * LRP + v, &nf[v]);
+            } else {
+                rinv = rcp_t(r[ck]);  // every lane holds whole rows: column k is local
+#pragma unroll
+                for (int li = 0; li < LR; ++li) nf[li] = -(a[li][ck] * rinv);
+                nf[lk] = sel_t(own_row, T(0), nf[lk]);
+            }
+            // slot k now belongs to column k of the augmented identity
+            r[ck] = sel_t(own_col, T(1), r[ck]);
+            const T diag = sel_t(own_row, T(1), T(0));
+#pragma unroll
+            for (int li = 0; li < LR; ++li) a[li][ck] = sel_t(own_col, (li == lk) ? diag : T(0), a[li][ck]);
+#pragma unroll
+            for (int li = 0; li < LR; ++li) row_update<LC>(a[li], r, nf[li]);
+            dinv[lk] = sel_t(own_row, rinv, dinv[lk]);
+        }
+
+        // ---- scale by 1/pivot, undo the row permutation as a column scatter -------------------
+        __syncwarp();
+#pragma unroll
+        for (int li = 0; li < LR; ++li) {
+#pragma unroll
+            for (int lj = 0; lj < LC; ++lj) a[li][lj] *= dinv[li];
+        }
+        if (MODE == kModeNone) {
+#pragma unroll
+            for (int li = 0; li < LR; ++li) {
+                const int i = li * GR + gr;
+                const bool rok = (li * GR + GR - 1 < N) || (i < N);
+#pragma unroll
+                for (int q = 0; q < CPL; ++q) {
+                    const int cq = q * GC + gc;
+                    if (rok && ((q * GC + GC - 1 < CPR) || (cq < CPR))) st_vec<T, CH>(mimg + i * P + cq * CH, &a[li][q * CH]);
+                }
+            }
+        } else {
+            int pcol[LC];
+#pragma unroll
+            for (int q = 0; q < CPL; ++q) {
+                const int cq = q * GC + gc;
+                const bool ok = (q * GC + GC - 1 < CPR) || (cq < CPR);
+#pragma unroll
+                for (int w = 0; w < CH; ++w) pcol[q * CH + w] = ok ? perm[cq * CH + w] : -1;
+            }
+#pragma unroll
+            for (int li = 0; li < LR; ++li) {
+                const int i = li * GR + gr;
+                const bool rok = (li * GR + GR - 1 < N) || (i < N);
+#pragma unroll
+                for (int lj = 0; lj < LC; ++lj)
+                    if (rok && pcol[lj] >= 0) mimg[i * P + pcol[lj]] = a[li][lj];
+            }
+        }
+        __syncwarp();
+        if constexpr (L::ROWVEC) copy_out_padded<T, L, N>(gspan, wbase, nm * N * L::CPR16, lane);
+        else copy_out<T>(gspan, img, nm * N * N, lane);
+        int32_t* pivp = piv;
+        asm volatile("" : "+l"(pivp));  // opaque: keeps the compiler from cloning the whole tile loop on piv == NULL
+        if (pivp != nullptr) {
+            int32_t* pdst = pivp + first * N;
+            for (int e = lane; e < nm * N; e += 32)
+                pdst[e] = (MODE != kModeNone) ? perm_all[e] : (e % N);
+        }
+        __syncwarp();
+    }
+}
+
+}  // namespace lub

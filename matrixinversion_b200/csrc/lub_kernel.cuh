@@ -73,7 +73,7 @@ __device__ __forceinline__ void st_stream16(void* p, uint4 v) { __stcs(reinterpr
 // slots holding the same (maximal) value the LOWEST rank is the one the tree returns.
 // Bit l of the rank = "moved at tree level l" (level 0 = widest stride); a slot that stays
 // put wins the tie at that level, and later levels dominate earlier ones.
-__host__ __device__ inline int tree_slot_rank(int t, int tpm) {
+__host__ __device__ constexpr int tree_slot_rank(int t, int tpm) {
     int loc = t, rank = 0, lvl = 0;
     for (int s = tpm / 2; s > 0; s >>= 1, ++lvl) {
         if (loc >= 2 * s) return -1;

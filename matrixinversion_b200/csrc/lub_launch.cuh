@@ -5,6 +5,8 @@
 // driver (templated/run.py:201-223).
 #pragma once
 #include "lub_kernel.cuh"
+#include "lub_fast.cuh"
+#include "lub_v3.cuh"
 
 namespace lub {
 
@@ -52,59 +54,116 @@ struct AutoCfg {
     static constexpr int GR = c.gr, GC = c.gc;
 };
 
+// Layout choice for the v3 kernel.  Cost model measured on B200 (profiles/): the shared-memory
+// crossbar (shuffles included) moves one word per lane per cycle, so the per-step exchange
+// costs LR + LC shuffles per tile and a matrix should sit on as few lanes as its register
+// block allows.  Smallest G whose LR x LC block fits the element budget; among its splits the
+// one with the least exchange, then the fewest rows (per-row selects).
+constexpr Cfg pick_v3_cfg(int n, int es, bool pivoting) {
+    const int epv = 16 / es;
+    const int chv = (n % epv == 0) ? epv : ((epv == 4 && n % 2 == 0) ? 2 : 1);
+    const int ch = pivoting ? 1 : chv;
+    const int cpr = n / ch;
+    const int budget = (es == 4) ? 64 : 32;
+    for (int g = 1; g <= 32; g *= 2) {
+        if (g == 2) continue;  // two-lane groups never won a sweep
+        int best_cost = 1 << 30;
+        Cfg best{0, 0};
+        for (int gr = 1; gr <= g; gr *= 2) {
+            const int gc = g / gr;
+            const int lr = cdiv(n, gr), lc = cdiv(cpr, gc) * ch;
+            if (lr * lc > budget) continue;
+            const int cost = 64 * ((gc > 1 ? lr : 0) + (gr > 1 ? lc : 0)) + lr;
+            if (cost < best_cost) { best_cost = cost; best = Cfg{gr, gc}; }
+        }
+        if (best.gr) return best;
+    }
+    return Cfg{4, 8};
+}
+
+template <typename T, int N, int MODE>
+struct V3Cfg {
+#if defined(LUB_FORCE_GR) && defined(LUB_FORCE_GC)
+    static constexpr int GR = LUB_FORCE_GR, GC = LUB_FORCE_GC;
+#else
+    static constexpr Cfg c = pick_v3_cfg(N, (int)sizeof(T), MODE != kModeNone);
+    static constexpr int GR = c.gr, GC = c.gc;
+#endif
+    static constexpr int MINB = 2;  // 128 registers per thread, two 256-thread blocks per SM
+};
+
 constexpr int kMaxDevices = 64;
+
+struct KernelCache { int ready_threads; int blocks_per_sm; int sms; int regs; };
+
+template <typename K>
+cudaError_t prepare(K kern, KernelCache& c, int dev, int threads, int smem) {
+    if (c.ready_threads == threads) return cudaSuccess;
+    cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (err != cudaSuccess) return err;
+    int occ = 0;
+    err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, threads, smem);
+    if (err != cudaSuccess) return err;
+    if (occ < 1) return cudaErrorLaunchOutOfResources;
+    int sms = 0;
+    err = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (err != cudaSuccess) return err;
+    cudaFuncAttributes fa;
+    err = cudaFuncGetAttributes(&fa, kern);
+    if (err != cudaSuccess) return err;
+    c.blocks_per_sm = occ; c.sms = sms; c.regs = fa.numRegs; c.ready_threads = threads;
+    return cudaSuccess;
+}
 
 template <typename T, int N, int MODE>
 cudaError_t launch(void* A, int32_t* piv, long long batch, int threads, cudaStream_t stream,
                    LaunchInfo* info, int dry_run) {
-    constexpr int GR = AutoCfg<T, N, MODE>::GR, GC = AutoCfg<T, N, MODE>::GC;
-    using L = Layout<T, N, GR, GC, MODE>;
-    auto kern = lub_invert_kernel<T, N, GR, GC, MODE>;
-
-    if (threads <= 0) threads = 128;
+    if (threads <= 0) threads = 256;
     const int warps = threads / 32;
-    const int smem = L::HEADER_BYTES + warps * L::WARP_BYTES;
-
     int dev = 0;
     cudaError_t err = cudaGetDevice(&dev);
     if (err != cudaSuccess) return err;
     if (dev < 0 || dev >= kMaxDevices) return cudaErrorInvalidDevice;
 
-    // per-device, per-thread-count cache of (attribute set, occupancy, SM count)
-    struct Cache { int ready_threads; int blocks_per_sm; int sms; int regs; };
-    static Cache cache[kMaxDevices] = {};
-    Cache& c = cache[dev];
-    if (c.ready_threads != threads) {
-        err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        if (err != cudaSuccess) return err;
-        int occ = 0;
-        err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, threads, smem);
-        if (err != cudaSuccess) return err;
-        if (occ < 1) return cudaErrorLaunchOutOfResources;
-        int sms = 0;
-        err = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        if (err != cudaSuccess) return err;
-        cudaFuncAttributes fa;
-        err = cudaFuncGetAttributes(&fa, kern);
-        if (err != cudaSuccess) return err;
-        c.blocks_per_sm = occ; c.sms = sms; c.regs = fa.numRegs; c.ready_threads = threads;
-    }
+    using VC = V3Cfg<T, N, MODE>;
+    using FL = V3Layout<T, N, VC::GR, VC::GC, MODE>;
+    using GL = Layout<T, N, AutoCfg<T, N, MODE>::GR, AutoCfg<T, N, MODE>::GC, MODE>;
+    // the fast kernel's vector accesses need a 16-byte aligned batch (cudaMalloc gives 256);
+    // anything else (a view starting mid-buffer at an odd element) takes the generic kernel
+    const bool fast = dry_run || (reinterpret_cast<uintptr_t>(A) % 16 == 0);
 
-    const long long ntiles = (batch + L::MPW - 1) / L::MPW;
+    static KernelCache cache_fast[kMaxDevices] = {}, cache_gen[kMaxDevices] = {};
+    int smem, mpw, g;
+    KernelCache* c;
+    if (fast) {
+        smem = FL::HEADER_BYTES + warps * FL::WARP_BYTES; mpw = FL::MPW; g = FL::G; c = &cache_fast[dev];
+        err = prepare(lub_v3_kernel<T, N, VC::GR, VC::GC, MODE, VC::MINB>, *c, dev, threads, smem);
+    } else {
+        smem = GL::HEADER_BYTES + warps * GL::WARP_BYTES; mpw = GL::MPW; g = GL::G; c = &cache_gen[dev];
+        err = prepare(lub_invert_kernel<T, N, AutoCfg<T, N, MODE>::GR, AutoCfg<T, N, MODE>::GC, MODE>, *c, dev, threads, smem);
+    }
+    if (err != cudaSuccess) return err;
+
+    const long long ntiles = (batch + mpw - 1) / mpw;
     long long blocks = (ntiles + warps - 1) / warps;
-    const long long resident = (long long)c.sms * c.blocks_per_sm;
+    const long long resident = (long long)c->sms * c->blocks_per_sm;
     if (blocks > resident) blocks = resident;  // persistent: every warp strides over tiles
     if (info) {
         info->threads_per_block = threads;
-        info->threads_per_matrix = L::G;
-        info->matrices_per_block = warps * L::MPW;
+        info->threads_per_matrix = g;
+        info->matrices_per_block = warps * mpw;
         info->num_blocks = blocks;
         info->dyn_smem_bytes = smem;
-        info->regs_per_thread = c.regs;
-        info->blocks_per_sm = c.blocks_per_sm;
+        info->regs_per_thread = c->regs;
+        info->blocks_per_sm = c->blocks_per_sm;
     }
     if (dry_run || batch == 0) return cudaSuccess;
-    kern<<<(unsigned)blocks, threads, smem, stream>>>(static_cast<T*>(A), piv, batch);
+    if (fast)
+        lub_v3_kernel<T, N, VC::GR, VC::GC, MODE, VC::MINB>
+            <<<(unsigned)blocks, threads, smem, stream>>>(static_cast<T*>(A), piv, batch);
+    else
+        lub_invert_kernel<T, N, AutoCfg<T, N, MODE>::GR, AutoCfg<T, N, MODE>::GC, MODE>
+            <<<(unsigned)blocks, threads, smem, stream>>>(static_cast<T*>(A), piv, batch);
     return cudaGetLastError();
 }
 

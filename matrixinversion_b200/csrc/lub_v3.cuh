@@ -1,0 +1,303 @@
+// lub_v3.cuh -- third-generation hot-path kernel.  Same algorithm and results as
+// lub_kernel.cuh / lub_fast.cuh; the data movement is re-planned around the cost model that
+// Nsight Compute measurements on B200 established (profiles/r01_*.md):
+//
+//   * the shared-memory crossbar delivers one 32-bit word per lane per cycle per SM, whatever
+//     the instruction: a 128-bit LDS/STS is four wavefronts (one per quarter-warp) even when
+//     every lane reads the same address, and a predicated store still pays for every quarter
+//     that has an active lane.  A shuffle is one wavefront per word too, but needs no store.
+//     => the per-step pivot row / column exchange uses shuffles (LR + LC + 1 wavefronts per
+//        tile step) instead of a shared-memory mailbox (twice that), and matrices are spread
+//        over as FEW lanes as the register file allows (exchange per matrix ~ GR + GC).
+//   * pivoting modes use an element-granular image with an ODD row stride, so the pivot
+//     search's column walk and the permuted row gather are bank-conflict free; the price is
+//     scalar instead of 128-bit shared-memory instructions, which cost the same wavefronts.
+//   * pivot_mode none keeps the 128-bit padded image of lub_fast.cuh.
+#pragma once
+#include "lub_fast.cuh"
+
+namespace lub {
+
+template <typename T, int N, int GR, int GC, int MODE>
+struct V3Layout {
+    static constexpr int ES = sizeof(T);
+    static constexpr int EW = ES / 4;
+    static constexpr int EPV = 16 / ES;
+    static constexpr bool SC = (MODE != kModeNone);  // element-granular image, odd row stride
+    static constexpr int CHV = (N % EPV == 0) ? EPV : ((EPV == 4 && N % 2 == 0) ? 2 : 1);
+    static constexpr int CH = SC ? 1 : CHV;
+    static constexpr int G = GR * GC;
+    static_assert(G >= 1 && G <= 32 && (32 % G) == 0, "G must divide 32");
+    static constexpr int MPW = 32 / G;
+    static constexpr int CPR = N / CH;
+    static constexpr int CPL = cdiv_(CPR, GC);  // chunks per lane: lane-col gc holds chunks [gc*CPL, (gc+1)*CPL)
+    static constexpr int LC = CPL * CH;
+    static constexpr int LR = cdiv_(N, GR);     // rows per lane, cyclic over GR
+    static constexpr bool ROWVEC = !SC && (CH == EPV);
+    static constexpr int P = SC ? (N | 1) : (ROWVEC ? N + pick_row_pad<T, N>() : N);
+    static constexpr int SLOTS = 32 / EW;
+    static constexpr int SC_TARGET = (SLOTS / MPW) > 0 ? (SLOTS / MPW) : 1;
+    static constexpr int MPAD = SC ? ((MPW == 1) ? 0 : ((SC_TARGET - (N * P) % SLOTS + SLOTS) % SLOTS))
+                                   : (ROWVEC ? pick_mat_pad<T, N, P, MPW>() : 0);
+    static constexpr int MS = N * P + MPAD;
+    static constexpr bool ALIGNED = ((MPW * N * N * ES) % 16) == 0;  // every tile span starts on 16 bytes
+    static constexpr int IMG_BYTES = roundup_(MPW * MS * ES, 16) + 16;
+    static constexpr int PERM_BYTES = SC ? roundup_(MPW * N * 4, 16) : 0;
+    static constexpr int WARP_BYTES = IMG_BYTES + PERM_BYTES;
+    static constexpr int HEADER_BYTES = 64;
+    static constexpr int CPR16 = N * ES / 16;
+    static constexpr int RPAD16 = (P - N) * ES / 16, MPAD16 = MPAD * ES / 16;
+};
+
+// image offset (elements) of flat element f of a tile span, element-granular image
+template <typename L, int N>
+__device__ __forceinline__ int sc_off(int f) {
+    const int rg = f / N;  // row index within the tile (constant divisor)
+    int o = f + rg * (L::P - N);
+    if (L::MPAD != 0) o += (rg / N) * L::MPAD;
+    return o;
+}
+
+template <typename T, typename L, int N>
+__device__ __forceinline__ void copy_in_scatter(T* __restrict__ img, const T* __restrict__ src, int total, int lane) {
+    constexpr int EPV = L::EPV;
+    int nhead = 0;
+    if (!L::ALIGNED) {
+        const unsigned mis = (unsigned)(reinterpret_cast<uintptr_t>(src) & 15u);
+        nhead = mis ? (int)((16u - mis) / sizeof(T)) : 0;
+        if (nhead > total) nhead = total;
+        if (lane < nhead) img[sc_off<L, N>(lane)] = src[lane];
+    }
+    const int nvec = (total - nhead) / EPV;
+    const T* s = src + nhead;
+    auto put = [&](int q, uint4 v) {
+        const T* e = reinterpret_cast<const T*>(&v);
+        const int f0 = nhead + q * EPV;
+        if (L::ALIGNED && (N % EPV) == 0) {
+            const int o = sc_off<L, N>(f0);  // a 16-byte chunk never straddles a row
+#pragma unroll
+            for (int w = 0; w < EPV; ++w) img[o + w] = e[w];
+        } else {
+#pragma unroll
+            for (int w = 0; w < EPV; ++w) img[sc_off<L, N>(f0 + w)] = e[w];
+        }
+    };
+    int q = lane;
+    for (; q + 96 < nvec; q += 128) {
+        const uint4 v0 = ld_stream16(s + (size_t)q * EPV), v1 = ld_stream16(s + (size_t)(q + 32) * EPV);
+        const uint4 v2 = ld_stream16(s + (size_t)(q + 64) * EPV), v3 = ld_stream16(s + (size_t)(q + 96) * EPV);
+        put(q, v0); put(q + 32, v1); put(q + 64, v2); put(q + 96, v3);
+    }
+    for (; q < nvec; q += 32) put(q, ld_stream16(s + (size_t)q * EPV));
+    const int tb = nhead + nvec * EPV;
+    if (lane < total - tb) img[sc_off<L, N>(tb + lane)] = src[tb + lane];
+}
+
+template <typename T, typename L, int N>
+__device__ __forceinline__ void copy_out_gather(T* __restrict__ dst, const T* __restrict__ img, int total, int lane) {
+    constexpr int EPV = L::EPV;
+    int nhead = 0;
+    if (!L::ALIGNED) {
+        const unsigned mis = (unsigned)(reinterpret_cast<uintptr_t>(dst) & 15u);
+        nhead = mis ? (int)((16u - mis) / sizeof(T)) : 0;
+        if (nhead > total) nhead = total;
+        if (lane < nhead) dst[lane] = img[sc_off<L, N>(lane)];
+    }
+    const int nvec = (total - nhead) / EPV;
+    T* d = dst + nhead;
+    for (int q = lane; q < nvec; q += 32) {
+        uint4 v;
+        T* e = reinterpret_cast<T*>(&v);
+        const int f0 = nhead + q * EPV;
+        if (L::ALIGNED && (N % EPV) == 0) {
+            const int o = sc_off<L, N>(f0);
+#pragma unroll
+            for (int w = 0; w < EPV; ++w) e[w] = img[o + w];
+        } else {
+#pragma unroll
+            for (int w = 0; w < EPV; ++w) e[w] = img[sc_off<L, N>(f0 + w)];
+        }
+        st_stream16(d + (size_t)q * EPV, v);
+    }
+    const int tb = nhead + nvec * EPV;
+    if (lane < total - tb) dst[tb + lane] = img[sc_off<L, N>(tb + lane)];
+}
+
+// BSYNC: one block barrier per tile (see the loop).  DBG (tuning harness only): 1 = skip the
+// elimination, 2 = skip the pivot pre-pass (identity permutation), 4 = skip global loads/stores
+// after the first tile.  DBG is 0 in the product.
+template <typename T, int N, int GR, int GC, int MODE, int MINB = 1, bool BSYNC = true, int DBG = 0>
+__global__ void __launch_bounds__(kMaxThreads, MINB)
+lub_v3_kernel(T* __restrict__ A, int32_t* __restrict__ piv, long long batch) {
+    using L = V3Layout<T, N, GR, GC, MODE>;
+    constexpr int G = L::G, MPW = L::MPW, LR = L::LR, LC = L::LC, CH = L::CH, CPL = L::CPL, CPR = L::CPR;
+    constexpr int P = L::P, MS = L::MS;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    const int nwarps = blockDim.x >> 5;
+    int8_t* slot_rank = reinterpret_cast<int8_t*>(smem_raw);
+    unsigned char* wbase = smem_raw + L::HEADER_BYTES + (size_t)warp * L::WARP_BYTES;
+    int* perm_all = reinterpret_cast<int*>(wbase + L::IMG_BYTES);
+
+    if (MODE == kModeParallel) {
+        if (threadIdx.x < N) slot_rank[threadIdx.x] = (int8_t)tree_slot_rank(threadIdx.x, N);
+        __syncthreads();
+    }
+
+    const int g = lane % G;
+    const int ml = lane / G;
+    const int gr = g / GC;
+    const int gc = g % GC;
+    const int grp_base = ml * G;
+
+    const long long ntiles = (batch + MPW - 1) / MPW;
+#pragma unroll 1
+    for (long long tbase = (long long)blockIdx.x * nwarps; tbase < ntiles; tbase += (long long)gridDim.x * nwarps) {
+        // Re-align the block's warps once per tile: they all run the same ~50 KB of straight-line
+        // code, and warps that drift apart thrash the instruction caches (no_instruction stalls).
+        if (BSYNC) __syncthreads();
+        const long long tile = tbase + warp;
+        if (tile >= ntiles) continue;
+        const long long first = tile * MPW;
+        const int nm = (batch - first < MPW) ? (int)(batch - first) : MPW;
+        T* gspan = A + first * (long long)(N * N);
+        T* img;
+        if ((DBG & 4) && tile >= (long long)gridDim.x * nwarps) {
+            img = reinterpret_cast<T*>(wbase);
+        } else if constexpr (L::SC) {
+            img = reinterpret_cast<T*>(wbase);
+            copy_in_scatter<T, L, N>(img, gspan, nm * N * N, lane);
+        } else if constexpr (L::ROWVEC) {
+            img = reinterpret_cast<T*>(wbase);
+            copy_in_padded<T, L, N>(wbase, gspan, nm * N * L::CPR16, lane);
+        } else {
+            const unsigned mis = (unsigned)(reinterpret_cast<uintptr_t>(gspan) & 15u);
+            img = reinterpret_cast<T*>(wbase + mis);
+            copy_in<T>(img, gspan, nm * N * N, nm * N * N, lane);
+        }
+        __syncwarp();
+
+        T* mimg = img + ml * MS;
+        int* perm = perm_all + ml * N;
+        if ((DBG & 2) && MODE != kModeNone) {
+            for (int e = lane; e < MPW * N; e += 32) perm_all[e] = e % N;
+            __syncwarp();
+        } else if (MODE != kModeNone) {
+            if (N > 16) {
+                constexpr int MI = (MPW < 4) ? MPW : 4;
+#pragma unroll 1
+                for (int m = 0; m < MPW; m += MI)
+                    prepass_warp<T, N, MODE, P, MS, MI>(img + m * MS, perm_all + m * N, slot_rank, lane);
+            } else {
+                prepass_group<T, N, G, MODE, P>(mimg, perm, slot_rank, g);
+            }
+            __syncwarp();
+        }
+
+        // ---- registers <- image: rows permuted, LR x LC block per lane ---------------------
+        T a[LR][LC];
+#pragma unroll
+        for (int li = 0; li < LR; ++li) {
+            const int i = li * GR + gr;
+            const bool rok = (li * GR + GR - 1 < N) || (i < N);
+            int prow = i;
+            if (MODE != kModeNone) prow = rok ? perm[i] : 0;
+            const T* rowp = mimg + prow * P;
+#pragma unroll
+            for (int q = 0; q < CPL; ++q) {
+                const int cq = gc * CPL + q;
+                const bool ok = rok && ((GC * CPL <= CPR) || (cq < CPR));
+                if (ok) {
+                    ld_vec<T, CH>(rowp + cq * CH, &a[li][q * CH]);
+                } else {
+#pragma unroll
+                    for (int w = 0; w < CH; ++w) a[li][q * CH + w] = T(0);
+                }
+            }
+        }
+
+        // ---- Gauss-Jordan with deferred row scaling; exchange by shuffles ---------------------
+        T dinv[LR];
+#pragma unroll
+        for (int li = 0; li < LR; ++li) dinv[li] = T(0);
+#pragma unroll
+        for (int k = 0; k < ((DBG & 1) ? 0 : N); ++k) {
+            const int gro = k % GR, lk = k / GR;
+            const int cj = k / CH, gco = cj / CPL, ck = (cj % CPL) * CH + (k % CH);
+            const bool own_row = (GR == 1) || (gr == gro);
+            const bool own_col = (GC == 1) || (gc == gco);
+            T r[LC], c[LR];
+#pragma unroll
+            for (int lj = 0; lj < LC; ++lj)
+                r[lj] = (GR > 1) ? shfl_t(a[lk][lj], grp_base + gro * GC + gc) : a[lk][lj];
+#pragma unroll
+            for (int li = 0; li < LR; ++li)
+                c[li] = (GC > 1) ? shfl_t(a[li][ck], grp_base + gr * GC + gco) : a[li][ck];
+            const T pv = (GC > 1) ? shfl_t(r[ck], grp_base + gr * GC + gco) : r[ck];
+            const T rinv = rcp_t(pv);
+            set_if(own_col, r[ck], T(1));
+            T nf[LR];
+#pragma unroll
+            for (int li = 0; li < LR; ++li) nf[li] = -(c[li] * rinv);
+            set_if(own_row, nf[lk], T(0));
+            const T diag = sel_t(own_row, T(1), T(0));
+#pragma unroll
+            for (int li = 0; li < LR; ++li) set_if(own_col, a[li][ck], (li == lk) ? diag : T(0));
+#pragma unroll
+            for (int li = 0; li < LR; ++li) row_update<LC>(a[li], r, nf[li]);
+            set_if(own_row, dinv[lk], rinv);
+        }
+
+        // ---- scale by 1/pivot, undo the row permutation as a column scatter -------------------
+        __syncwarp();
+#pragma unroll
+        for (int li = 0; li < LR; ++li) {
+#pragma unroll
+            for (int lj = 0; lj < LC; ++lj) a[li][lj] *= ((DBG & 1) ? T(1) : dinv[li]);
+        }
+        if (MODE == kModeNone) {
+#pragma unroll
+            for (int li = 0; li < LR; ++li) {
+                const int i = li * GR + gr;
+                const bool rok = (li * GR + GR - 1 < N) || (i < N);
+#pragma unroll
+                for (int q = 0; q < CPL; ++q) {
+                    const int cq = gc * CPL + q;
+                    if (rok && ((GC * CPL <= CPR) || (cq < CPR))) st_vec<T, CH>(mimg + i * P + cq * CH, &a[li][q * CH]);
+                }
+            }
+        } else {
+            int pcol[LC];
+#pragma unroll
+            for (int lj = 0; lj < LC; ++lj) {
+                const int j = gc * LC + lj;
+                pcol[lj] = ((GC * LC <= N) || (j < N)) ? perm[j] : -1;
+            }
+#pragma unroll
+            for (int li = 0; li < LR; ++li) {
+                const int i = li * GR + gr;
+                const bool rok = (li * GR + GR - 1 < N) || (i < N);
+#pragma unroll
+                for (int lj = 0; lj < LC; ++lj)
+                    if (rok && pcol[lj] >= 0) mimg[i * P + pcol[lj]] = a[li][lj];
+            }
+        }
+        __syncwarp();
+        if ((DBG & 4) && tile >= (long long)gridDim.x * nwarps) {
+        } else if constexpr (L::SC) copy_out_gather<T, L, N>(gspan, img, nm * N * N, lane);
+        else if constexpr (L::ROWVEC) copy_out_padded<T, L, N>(gspan, wbase, nm * N * L::CPR16, lane);
+        else copy_out<T>(gspan, img, nm * N * N, lane);
+        int32_t* pivp = piv;
+        asm volatile("" : "+l"(pivp));  // opaque: keeps the compiler from cloning the whole tile loop on piv == NULL
+        if (pivp != nullptr) {
+            int32_t* pdst = pivp + first * N;
+            for (int e = lane; e < nm * N; e += 32)
+                pdst[e] = (MODE != kModeNone) ? perm_all[e] : (e % N);
+        }
+        __syncwarp();
+    }
+}
+
+}  // namespace lub

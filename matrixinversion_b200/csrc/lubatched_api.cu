@@ -190,7 +190,7 @@ int lu_batched_set_threads(int numthreads) {
 
 int lu_batched_get_threads(int n, int dtype) {
     (void)n; (void)dtype;
-    return g_threads ? g_threads : 128;
+    return g_threads ? g_threads : 256;
 }
 
 int lu_batched_enable_timing(int on) {

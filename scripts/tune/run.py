@@ -1,0 +1,60 @@
+#!/usr/bin/env python3
+"""Time every variant of scripts/tune/libtune.so; check each against the product library."""
+import argparse, ctypes, json, os, sys
+import numpy as np
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+import torch
+import matrixinversion_b200 as lub
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--batch", type=int, default=1_000_000)
+ap.add_argument("--threads", default="128")
+ap.add_argument("--iters", type=int, default=4)
+ap.add_argument("--only", default="")
+a = ap.parse_args()
+T = ctypes.CDLL(os.path.join(os.path.dirname(os.path.abspath(__file__)), "libtune.so"))
+T.tune_name.restype = ctypes.c_char_p
+T.tune_launch.argtypes = [ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_longlong, ctypes.c_int, ctypes.c_void_p,
+                          ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_int)]
+cache = {}
+for i in range(T.tune_count()):
+    name = T.tune_name(i).decode()
+    if a.only and a.only not in name:
+        continue
+    parts = name.split()
+    tdt = torch.float32 if parts[0] == "float" else torch.float64
+    n = int(parts[1][2:]); mode = int(parts[3][4:])
+    key = (tdt, n, mode)
+    if key not in cache:
+        cache.clear()
+        g = torch.Generator(device="cuda").manual_seed(n)
+        A0 = torch.rand((a.batch, n, n), generator=g, device="cuda", dtype=tdt)
+        if mode == 0:
+            A0 += n * torch.eye(n, device="cuda", dtype=tdt)
+        ref = A0.clone(); pref = torch.empty((a.batch, n), dtype=torch.int32, device="cuda")
+        lub.lu_batched_inplace(ref, pref, mode)
+        cache[key] = (A0, ref, pref)
+    A0, ref, pref = cache[key]
+    for threads in [int(t) for t in a.threads.split(",")]:
+        A = A0.clone(); piv = torch.empty_like(pref)
+        occ, blocks = ctypes.c_int(), ctypes.c_int()
+        best = 1e9
+        ok = True
+        for it in range(a.iters + 1):
+            A.copy_(A0)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            rc = T.tune_launch(i, A.data_ptr(), piv.data_ptr() if it == 0 else None, a.batch, threads,
+                               torch.cuda.current_stream().cuda_stream, ctypes.byref(occ), ctypes.byref(blocks))
+            e1.record(); torch.cuda.synchronize()
+            if rc != 0:
+                ok = False; break
+            if it == 0:
+                same = bool(torch.equal(piv, pref))
+                close = bool(torch.allclose(A, ref, rtol=1e-3, atol=1e-3, equal_nan=True))
+            else:
+                best = min(best, e0.elapsed_time(e1))
+        es = 4 if tdt == torch.float32 else 8
+        print(json.dumps({"variant": name, "threads": threads, "ok": ok, "ms": round(best, 4), "occ_blocks": occ.value,
+                          "GBps": round(2 * n * n * es * a.batch / best / 1e6), "piv_equal": same, "values_close": close}), flush=True)

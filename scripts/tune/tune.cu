@@ -1,0 +1,57 @@
+// Dev-only tuning harness (not part of the product library): explicit instantiations of the
+// fast kernel for a handful of lane layouts, launched by index so that scripts/tune/run.py can
+// time them side by side on the GPU box.  Build: make -C scripts/tune
+#include <cstdio>
+#include "../../matrixinversion_b200/csrc/lub_v3.cuh"
+
+using namespace lub;
+
+struct Variant {
+    const char* name;
+    int mpw, warp_bytes, header;
+    void (*set_attr)(int smem);
+    void (*launch)(void*, int*, long long, unsigned, int, int, cudaStream_t);
+    int (*occ)(int threads, int smem);
+};
+
+template <typename T, int N, int GR, int GC, int MODE, int MINB, int DBG = 0>
+struct V {
+    using L = V3Layout<T, N, GR, GC, MODE>;
+    static void set_attr(int smem) {
+        cudaFuncSetAttribute(lub_v3_kernel<T, N, GR, GC, MODE, MINB, (DBG & 8) != 0, (DBG & 7)>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    }
+    static void launch(void* A, int* piv, long long batch, unsigned blocks, int threads, int smem, cudaStream_t s) {
+        lub_v3_kernel<T, N, GR, GC, MODE, MINB, (DBG & 8) != 0, (DBG & 7)><<<blocks, threads, smem, s>>>((T*)A, piv, batch);
+    }
+    static int occ(int threads, int smem) {
+        int o = 0;
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, lub_v3_kernel<T, N, GR, GC, MODE, MINB, (DBG & 8) != 0, (DBG & 7)>, threads, smem);
+        return o;
+    }
+    static Variant make(const char* name) { return Variant{name, L::MPW, L::WARP_BYTES, L::HEADER_BYTES, set_attr, launch, occ}; }
+};
+
+#define VAR(T, N, GR, GC, MODE, MINB) V<T, N, GR, GC, MODE, MINB>::make(#T " N=" #N " " #GR "x" #GC " mode" #MODE " minb" #MINB)
+#define VARD(T, N, GR, GC, MODE, MINB, DBG) V<T, N, GR, GC, MODE, MINB, DBG>::make(#T " N=" #N " " #GR "x" #GC " mode" #MODE " minb" #MINB " dbg" #DBG)
+
+static Variant variants[] = {
+#include "variants.inc"
+};
+
+extern "C" int tune_count() { return (int)(sizeof(variants) / sizeof(variants[0])); }
+extern "C" const char* tune_name(int i) { return variants[i].name; }
+extern "C" int tune_launch(int i, void* A, int* piv, long long batch, int threads, void* stream, int* occ_out, int* blocks_out) {
+    Variant& v = variants[i];
+    const int warps = threads / 32;
+    const int smem = v.header + warps * v.warp_bytes;
+    v.set_attr(smem);
+    const int occ = v.occ(threads, smem);
+    if (occ < 1) return -1;
+    const long long ntiles = (batch + v.mpw - 1) / v.mpw;
+    long long blocks = (ntiles + warps - 1) / warps;
+    if (blocks > 148ll * occ) blocks = 148ll * occ;
+    if (occ_out) *occ_out = occ;
+    if (blocks_out) *blocks_out = (int)blocks;
+    v.launch(A, piv, batch, (unsigned)blocks, threads, smem, (cudaStream_t)stream);
+    return cudaGetLastError() == cudaSuccess ? 0 : -2;
+}
