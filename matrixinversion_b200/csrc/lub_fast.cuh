@@ -194,6 +194,17 @@ __device__ __forceinline__ unsigned long long warp_max_bits(unsigned long long v
     return ((unsigned long long)mh << 32) | ml;
 }
 
+template <typename T, int N, int G, int MODE, int P>
+__device__ __forceinline__ void prepass_group(const T* __restrict__ mimg, int* __restrict__ perm,
+                                              const int8_t* __restrict__ slot_rank, int g);
+
+// Exact but slow warp-wide search (explicit priorities, butterfly reductions); out of line so
+// that its code stays off the hot path.
+template <typename T, int N, int MODE, int P>
+__device__ __noinline__ void prepass_exact(const T* mimg, int* perm, const int8_t* slot_rank, int lane) {
+    prepass_group<T, N, 32, MODE, P>(mimg, perm, slot_rank, lane);
+}
+
 // MI matrices are searched in lock step: their dependency chains (LDS -> REDUX -> VOTE -> SHFL)
 // are independent, so the scheduler overlaps them.
 template <typename T, int N, int MODE, int P, int MS, int MI>
@@ -203,14 +214,16 @@ __device__ __forceinline__ void prepass_warp(const T* __restrict__ img0, int* __
     constexpr unsigned ALL = (N >= 32) ? 0xffffffffu : ((1u << N) - 1u);
     constexpr unsigned REACH = ReachMask<N>::value;
     int prow[MI];  // original row sitting at position `lane`
+    unsigned multi[MI];
 #pragma unroll
-    for (int m = 0; m < MI; ++m) prow[m] = (lane < N) ? lane : 0;
+    for (int m = 0; m < MI; ++m) { prow[m] = (lane < N) ? lane : 0; multi[m] = 0u; }
 #pragma unroll
     for (int k = 0; k < N - 1; ++k) {
         // rows this step may pick: serial = every row below k; parallel = the slots the
         // reference tree merges into slot 0 (slot t <-> row k+1+t), plus the seed row k
         const unsigned vmask = ((MODE == kModeParallel) ? ((REACH << (k + 1)) | (1u << k)) : (ALL << k)) & ALL;
-        const bool valid = (vmask >> lane) & 1u;
+        // (when every slot is reachable the mask is just "position >= k")
+        const bool valid = (vmask == ((ALL << k) & ALL)) ? (lane >= k && lane < N) : (((vmask >> lane) & 1u) != 0u);
         U v[MI], mx[MI];
         unsigned bal[MI];
 #pragma unroll
@@ -221,21 +234,15 @@ __device__ __forceinline__ void prepass_warp(const T* __restrict__ img0, int* __
         for (int m = 0; m < MI; ++m) bal[m] = __ballot_sync(0xffffffffu, valid && v[m] == mx[m]);
 #pragma unroll
         for (int m = 0; m < MI; ++m) {
-            int wl;
-            if (MODE == kModeSerial) {
-                wl = __ffs(bal[m]) - 1;  // lowest row among the maxima; row k itself if it ties (strict '>')
-            } else {
-                if (bal[m] & (1u << k)) {
-                    wl = k;  // nothing strictly larger than |A[k][k]|
-                } else if ((bal[m] & (bal[m] - 1u)) == 0u) {
-                    wl = __ffs(bal[m]) - 1;
-                } else {  // equal maxima in several slots: the tree keeps the lowest rank
-                    const bool cand = (bal[m] >> lane) & 1u;
-                    const unsigned rk = cand ? (unsigned)slot_rank[cand ? lane - k - 1 : 0] : 0xffu;
-                    const unsigned best = __reduce_min_sync(0xffffffffu, rk);
-                    wl = __ffs(__ballot_sync(0xffffffffu, rk == best)) - 1;
-                }
-            }
+            // Lowest position among the maxima.  Serial mode: that IS find_pivot's answer (strict
+            // '>' from the seed row k upwards).  Parallel mode: identical whenever the maximum is
+            // unique or row k itself (the seed every tree slot starts from) is among the maxima.
+            // Equal maxima in several OTHER slots need the tree's rank order; any step with more
+            // than one maximum is only flagged here (no branch in this loop: a branch per step
+            // costs the scheduler the overlap between the MI chains) and such a matrix is redone
+            // with the exact search afterwards.
+            const int wl = __ffs(bal[m]) - 1;
+            if (MODE == kModeParallel) multi[m] |= bal[m] & (bal[m] - 1u);  // non-zero <=> two or more maxima
             // swap the row ids of positions k and wl (a no-op when wl == k)
             const int other = __shfl_sync(0xffffffffu, prow[m], lane == k ? wl : k);
             prow[m] = (lane == k || lane == wl) ? other : prow[m];
@@ -244,6 +251,14 @@ __device__ __forceinline__ void prepass_warp(const T* __restrict__ img0, int* __
 #pragma unroll
     for (int m = 0; m < MI; ++m)
         if (lane < N) perm0[m * N + lane] = prow[m];
+    if (MODE == kModeParallel) {
+#pragma unroll
+        for (int m = 0; m < MI; ++m)
+            if (multi[m] != 0u) {  // warp-uniform, rare (needs two equal |values| in one column)
+                __syncwarp();
+                prepass_exact<T, N, MODE, P>(img0 + m * MS, perm0 + m * N, slot_rank, lane);
+            }
+    }
 }
 
 // generic sub-warp pre-pass on a strided image (N <= 16): see pivot_prepass in lub_kernel.cuh

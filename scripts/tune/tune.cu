@@ -2,7 +2,7 @@
 // fast kernel for a handful of lane layouts, launched by index so that scripts/tune/run.py can
 // time them side by side on the GPU box.  Build: make -C scripts/tune
 #include <cstdio>
-#include "../../matrixinversion_b200/csrc/lub_v3.cuh"
+#include "../../matrixinversion_b200/csrc/lub_v4.cuh"
 
 using namespace lub;
 
@@ -16,16 +16,16 @@ struct Variant {
 
 template <typename T, int N, int GR, int GC, int MODE, int MINB, int DBG = 0>
 struct V {
-    using L = V3Layout<T, N, GR, GC, MODE>;
+    using L = V4Layout<T, N, GR, GC, MODE>;
     static void set_attr(int smem) {
-        cudaFuncSetAttribute(lub_v3_kernel<T, N, GR, GC, MODE, MINB, (DBG & 8) != 0, (DBG & 7)>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        cudaFuncSetAttribute(lub_v4_kernel<T, N, GR, GC, MODE, MINB, (DBG & 8) != 0, (DBG & 23)>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     }
     static void launch(void* A, int* piv, long long batch, unsigned blocks, int threads, int smem, cudaStream_t s) {
-        lub_v3_kernel<T, N, GR, GC, MODE, MINB, (DBG & 8) != 0, (DBG & 7)><<<blocks, threads, smem, s>>>((T*)A, piv, batch);
+        lub_v4_kernel<T, N, GR, GC, MODE, MINB, (DBG & 8) != 0, (DBG & 23)><<<blocks, threads, smem, s>>>((T*)A, piv, batch);
     }
     static int occ(int threads, int smem) {
         int o = 0;
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, lub_v3_kernel<T, N, GR, GC, MODE, MINB, (DBG & 8) != 0, (DBG & 7)>, threads, smem);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, lub_v4_kernel<T, N, GR, GC, MODE, MINB, (DBG & 8) != 0, (DBG & 23)>, threads, smem);
         return o;
     }
     static Variant make(const char* name) { return Variant{name, L::MPW, L::WARP_BYTES, L::HEADER_BYTES, set_attr, launch, occ}; }
