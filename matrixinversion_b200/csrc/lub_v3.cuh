@@ -235,7 +235,8 @@ lub_v3_kernel(T* __restrict__ A, int32_t* __restrict__ piv, long long batch) {
 #pragma unroll
             for (int li = 0; li < LR; ++li)
                 c[li] = (GC > 1) ? shfl_t(a[li][ck], grp_base + gr * GC + gco) : a[li][ck];
-            const T pv = (GC > 1) ? shfl_t(r[ck], grp_base + gr * GC + gco) : r[ck];
+            // straight from the owner (not via r[ck]): all shuffles of a step leave in one batch
+            const T pv = (G > 1) ? shfl_t(a[lk][ck], grp_base + gro * GC + gco) : a[lk][ck];
             const T rinv = rcp_t(pv);
             set_if(own_col, r[ck], T(1));
             T nf[LR];

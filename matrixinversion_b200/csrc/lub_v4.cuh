@@ -103,6 +103,7 @@ __global__ void __launch_bounds__(kMaxThreads, MINB)
 lub_v4_kernel(T* __restrict__ A, int32_t* __restrict__ piv, long long batch) {
     using L = V4Layout<T, N, GR, GC, MODE>;
     constexpr int G = L::G, MPW = L::MPW, LR = L::LR, LC = L::LC, GM = L::GM, P = L::P, MS = L::MS;
+    constexpr unsigned STAGGER_NS = (DBG >> 8) * 500u;  // tuning: DBG bits 8.. = stagger quantum in 0.5 us
     extern __shared__ __align__(16) unsigned char smem_raw[];
 
     const int lane = threadIdx.x & 31;
@@ -124,6 +125,13 @@ lub_v4_kernel(T* __restrict__ A, int32_t* __restrict__ piv, long long batch) {
     const int grp_base = ml * G;
 
     const long long ntiles = (batch + MPW - 1) / MPW;
+    // De-phase the resident warps once: they all start a tile (a memory-bound staging phase
+    // followed by an FMA-bound elimination phase) at the same instant, and with equal work per
+    // tile they would stay in step, leaving HBM idle while every warp computes and vice versa.
+    if (STAGGER_NS > 0) {
+        const unsigned slot = BSYNC ? (blockIdx.x / 148u) % 4u : (unsigned)(warp + blockIdx.x) % 4u;
+        if (slot) __nanosleep(slot * STAGGER_NS);
+    }
 #pragma unroll 1
     for (long long tbase = (long long)blockIdx.x * nwarps; tbase < ntiles; tbase += (long long)gridDim.x * nwarps) {
         // Re-align the block's warps once per tile: they all run the same straight-line code, and
@@ -195,7 +203,8 @@ lub_v4_kernel(T* __restrict__ A, int32_t* __restrict__ piv, long long batch) {
                 for (int lj = 0; lj < LC; ++lj) r[lj] = (GR > 1) ? shfl_t(a[lk][lj], src_row) : a[lk][lj];
 #pragma unroll
                 for (int li = 0; li < LR; ++li) c[li] = (GC > 1) ? shfl_t(a[li][ck], src_col) : a[li][ck];
-                const T pv = (GC > 1) ? shfl_t(r[ck], src_col) : r[ck];
+                // straight from the owner (not via r[ck]): all shuffles of a step leave in one batch
+                const T pv = (G > 1) ? shfl_t(a[lk][ck], grp_base + gro * GC + gco) : a[lk][ck];
                 const T rinv = rcp_t(pv);
                 // slot k now belongs to column k of the augmented identity: the broadcast row has
                 // a 1 there, and the column itself is cleared (mask 0) before the update

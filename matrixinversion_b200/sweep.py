@@ -1,0 +1,167 @@
+#!/usr/bin/env python3
+"""Sweep driver -- successor of the reference's per-variant `run.py`
+(/root/reference/templated/run.py:169-261), re-targeted from "recompile ./custom per
+configuration and parse its stdout" to calls into the C ABI via ctypes.
+
+What is kept:
+  * the loop: every matrix size in 1..32 x batch in {100000, 500000, 1000000} x 10 runs
+    (run.py:171-176); `--sizes/--batches/--runs` narrow it;
+  * one cold single launch per run, kernel time only from a CUDA event pair -- the
+    reference's timing convention (templated/luBatchedInplace.cu:71-82); `--warm` adds the
+    warm numbers next to it;
+  * the result schema and file names (run.py:236-250): benchmark_results/runtime_results/<100k|500k|1M>/
+    benchmark_results_<name>.json with key "m{N}_n{batch}_t{T}" ->
+    {matrix_size, num_matrices, num_threads, runtimes[ms], runtime_avg, variance, std_dev,
+    incorrect_inversions}, rewritten after every configuration, plus
+    benchmark_results_incomplete.json on an exception (run.py:252-260) -- so plot.py-style
+    consumers keep working;
+  * the NUMTHREADS table (run.py:201-223) is recorded as `reference_num_threads`; the
+    library picks its own launch geometry (`num_threads` is what it actually used).
+What is fixed: the reference's parser `break`s on the "Kernel execution time" line, which is
+printed before "Incorrect inversions", so its sweep never records correctness.
+Here `incorrect_inversions` is the verifyInv-compatible count of every run.
+Extra keys (additive): gbps, matrices_per_s, gflops_2n3, frac_hbm_roofline, cublas_ms (--cublas).
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes
+import json
+import os
+import shutil
+
+import numpy as np
+
+from . import _lib, api
+
+BATCH_NAMES = {100000: "100k", 500000: "500k", 1000000: "1M"}
+
+
+def create_output_directories(base="benchmark_results"):
+    """run.py:9-22."""
+    if os.path.exists(base):
+        shutil.rmtree(base)
+    ncu_dir, runtime_dir = os.path.join(base, "ncu_profiles"), os.path.join(base, "runtime_results")
+    os.makedirs(ncu_dir)
+    os.makedirs(runtime_dir)
+    return base, ncu_dir, runtime_dir
+
+
+def result_key(matrix_size, num_matrices, num_threads):
+    return "m%d_n%d_t%d" % (matrix_size, num_matrices, num_threads)
+
+
+def make_entry(matrix_size, num_matrices, num_threads, runtimes, incorrect, extra=None):
+    """The reference's per-configuration record (run.py:236-246)."""
+    e = {
+        "matrix_size": matrix_size,
+        "num_matrices": num_matrices,
+        "num_threads": num_threads,
+        "runtimes": [float(x) for x in runtimes],
+        "runtime_avg": float(sum(runtimes) / len(runtimes)),
+        "variance": float(np.var(runtimes)),
+        "std_dev": float(np.std(runtimes)),
+        "incorrect_inversions": [int(x) for x in incorrect if x > 0],
+    }
+    if extra:
+        e.update(extra)
+    return e
+
+
+def save_results(results, filepath):
+    with open(filepath, "w") as f:
+        json.dump(results, f, indent=4)
+
+
+def run_config(n, batch, mode, dtype, template, runs, warm=False, cublas=False, peak_gbps=None):
+    """`runs` cold single launches of one configuration; returns the JSON entry."""
+    import torch
+
+    tdt = torch.float32 if np.dtype(dtype) == np.float32 else torch.float64
+    dT = torch.from_numpy(np.ascontiguousarray(template)).cuda()
+    orig = dT.unsqueeze(0).expand(batch, n, n).contiguous()   # main()'s replicate loop
+    geo = api.geometry(n, batch, mode, dtype)
+    runtimes, incorrect, warm_ms = [], [], []
+    A = torch.empty_like(orig)
+    api.enable_timing(True)
+    try:
+        for r in range(runs):
+            A.copy_(orig)
+            torch.cuda.synchronize()
+            api.lu_batched_inplace(A, None, mode)
+            runtimes.append(api.last_kernel_ms())
+            _, bad, _ = api.verify_inv(orig, A)
+            incorrect.append(bad)
+        if warm:
+            for r in range(runs):
+                A.copy_(orig)
+                api.lu_batched_inplace(A, None, mode)
+                warm_ms.append(api.last_kernel_ms())
+    finally:
+        api.enable_timing(False)
+    es = np.dtype(dtype).itemsize
+    best = min(runtimes)
+    extra = {"reference_num_threads": api.default_num_threads(n), "threads_per_matrix": geo.threads_per_matrix,
+             "matrices_per_block": geo.matrices_per_block, "num_blocks": geo.num_blocks,
+             "matrices_per_s": batch / (best * 1e-3), "gbps": 2.0 * n * n * es * batch / (best * 1e-3) / 1e9,
+             "gflops_2n3": 2.0 * n ** 3 * batch / (best * 1e-3) / 1e9}
+    if peak_gbps:
+        extra["frac_hbm_roofline"] = extra["gbps"] / peak_gbps
+    if warm_ms:
+        extra["warm_runtimes"] = warm_ms
+    if cublas:
+        C = _lib.cublas_lib()
+        dst = torch.empty_like(orig)
+        t1, t2 = ctypes.c_float(), ctypes.c_float()
+        A.copy_(orig)
+        rc = C.lu_batched_cublas_baseline(A.data_ptr(), dst.data_ptr(), n, batch, 0 if tdt == torch.float32 else 1,
+                                          0 if api._mode(mode) == 0 else 1, ctypes.byref(t1), ctypes.byref(t2))
+        if rc == 0:
+            extra["cublas_ms"] = t1.value + t2.value
+            extra["cublas_getri_share"] = t2.value / (t1.value + t2.value)
+            extra["speedup_vs_cublas"] = (t1.value + t2.value) / best
+    return make_entry(n, batch, geo.threads_per_block, runtimes, incorrect, extra)
+
+
+def main(argv=None):
+    ap = argparse.ArgumentParser(description=__doc__, formatter_class=argparse.RawDescriptionHelpFormatter)
+    ap.add_argument("--variant", default="parallel_pivot", help="templated | serial_pivot | parallel_pivot (or none/serial/parallel)")
+    ap.add_argument("--input", default="mtrand32_new1.txt", help="template matrix text file (first N*N tokens are used)")
+    ap.add_argument("--dtype", default="float32", choices=["float32", "float64"])
+    ap.add_argument("--sizes", default="1-32")
+    ap.add_argument("--batches", default="100000,500000,1000000")
+    ap.add_argument("--runs", type=int, default=10)
+    ap.add_argument("--out", default="benchmark_results")
+    ap.add_argument("--warm", action="store_true")
+    ap.add_argument("--cublas", action="store_true")
+    ap.add_argument("--peak-gbps", type=float, default=None)
+    a = ap.parse_args(argv)
+
+    lo, _, hi = a.sizes.partition("-")
+    sizes = range(int(lo), int(hi or lo) + 1)
+    dtype = np.dtype(a.dtype)
+    base, ncu_dir, runtime_dir = create_output_directories(a.out)
+    results = {}
+    try:
+        for batch in [int(b) for b in a.batches.split(",")]:
+            name = BATCH_NAMES.get(batch, str(batch))
+            os.makedirs(os.path.join(ncu_dir, name), exist_ok=True)
+            out_dir = os.path.join(runtime_dir, name)
+            os.makedirs(out_dir, exist_ok=True)
+            results = {}
+            for n in sizes:
+                print("\nTesting configuration: Matrix Size=%d, Num Matrices=%d" % (n, batch))
+                template = api.read_template(a.input, n, dtype)
+                entry = run_config(n, batch, a.variant, dtype, template, a.runs, a.warm, a.cublas, a.peak_gbps)
+                print("Number of threads: %d" % entry["num_threads"])
+                results[result_key(n, batch, entry["num_threads"])] = entry
+                save_results(results, os.path.join(out_dir, "benchmark_results_%s.json" % name))
+    except Exception as e:  # keep what we have, like the reference (run.py:252-260)
+        print("Unexpected error: %s" % e)
+        save_results(results, os.path.join(runtime_dir, "benchmark_results_incomplete.json"))
+        raise
+    return 0
+
+
+if __name__ == "__main__":
+    raise SystemExit(main())

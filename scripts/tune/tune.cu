@@ -15,24 +15,42 @@ struct Variant {
 };
 
 template <typename T, int N, int GR, int GC, int MODE, int MINB, int DBG = 0>
-struct V {
-    using L = V4Layout<T, N, GR, GC, MODE>;
+struct V3 {
+    using L = V3Layout<T, N, GR, GC, MODE>;
     static void set_attr(int smem) {
-        cudaFuncSetAttribute(lub_v4_kernel<T, N, GR, GC, MODE, MINB, (DBG & 8) != 0, (DBG & 23)>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        cudaFuncSetAttribute(lub_v3_kernel<T, N, GR, GC, MODE, MINB, (DBG & 8) != 0, (DBG & 7)>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     }
     static void launch(void* A, int* piv, long long batch, unsigned blocks, int threads, int smem, cudaStream_t s) {
-        lub_v4_kernel<T, N, GR, GC, MODE, MINB, (DBG & 8) != 0, (DBG & 23)><<<blocks, threads, smem, s>>>((T*)A, piv, batch);
+        lub_v3_kernel<T, N, GR, GC, MODE, MINB, (DBG & 8) != 0, (DBG & 7)><<<blocks, threads, smem, s>>>((T*)A, piv, batch);
     }
     static int occ(int threads, int smem) {
         int o = 0;
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, lub_v4_kernel<T, N, GR, GC, MODE, MINB, (DBG & 8) != 0, (DBG & 23)>, threads, smem);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, lub_v3_kernel<T, N, GR, GC, MODE, MINB, (DBG & 8) != 0, (DBG & 7)>, threads, smem);
+        return o;
+    }
+    static Variant make(const char* name) { return Variant{name, L::MPW, L::WARP_BYTES, L::HEADER_BYTES, set_attr, launch, occ}; }
+};
+
+template <typename T, int N, int GR, int GC, int MODE, int MINB, int DBG = 0>
+struct V {
+    using L = V4Layout<T, N, GR, GC, MODE>;
+    static void set_attr(int smem) {
+        cudaFuncSetAttribute(lub_v4_kernel<T, N, GR, GC, MODE, MINB, (DBG & 8) != 0, (DBG & ~8)>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    }
+    static void launch(void* A, int* piv, long long batch, unsigned blocks, int threads, int smem, cudaStream_t s) {
+        lub_v4_kernel<T, N, GR, GC, MODE, MINB, (DBG & 8) != 0, (DBG & ~8)><<<blocks, threads, smem, s>>>((T*)A, piv, batch);
+    }
+    static int occ(int threads, int smem) {
+        int o = 0;
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, lub_v4_kernel<T, N, GR, GC, MODE, MINB, (DBG & 8) != 0, (DBG & ~8)>, threads, smem);
         return o;
     }
     static Variant make(const char* name) { return Variant{name, L::MPW, L::WARP_BYTES, L::HEADER_BYTES, set_attr, launch, occ}; }
 };
 
 #define VAR(T, N, GR, GC, MODE, MINB) V<T, N, GR, GC, MODE, MINB>::make(#T " N=" #N " " #GR "x" #GC " mode" #MODE " minb" #MINB)
-#define VARD(T, N, GR, GC, MODE, MINB, DBG) V<T, N, GR, GC, MODE, MINB, DBG>::make(#T " N=" #N " " #GR "x" #GC " mode" #MODE " minb" #MINB " dbg" #DBG)
+#define VARD(T, N, GR, GC, MODE, MINB, DBG) V<T, N, GR, GC, MODE, MINB, DBG>::make(#T " N=" #N " " #GR "x" #GC " mode" #MODE " minb" #MINB " dbg" #DBG " v4")
+#define VAR3(T, N, GR, GC, MODE, MINB, DBG) V3<T, N, GR, GC, MODE, MINB, DBG>::make(#T " N=" #N " " #GR "x" #GC " mode" #MODE " minb" #MINB " dbg" #DBG " v3")
 
 static Variant variants[] = {
 #include "variants.inc"

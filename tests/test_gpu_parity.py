@@ -290,3 +290,17 @@ def test_cublas_baseline_agrees():
         assert rc == 0
         X, _ = gpu_invert(A, 2)
         assert np.allclose(dX.cpu().numpy(), X, rtol=0, atol=(1e-5 if dtype == np.float32 else 1e-13))
+
+
+def test_sweep_driver_records_correctness(tmp_path, inputs):
+    """The run.py successor on the GPU: reference JSON schema, and -- unlike the reference's
+    parser -- `incorrect_inversions` is really recorded."""
+    from matrixinversion_b200 import sweep
+    e = sweep.run_config(18, 20000, "parallel_pivot", np.float32, template(inputs, "mtrand32_new1", 18), runs=2, cublas=True)
+    for k in ("matrix_size", "num_matrices", "num_threads", "runtimes", "runtime_avg", "variance", "std_dev", "incorrect_inversions"):
+        assert k in e
+    assert len(e["runtimes"]) == 2 and all(t > 0 for t in e["runtimes"]) and e["incorrect_inversions"] == []
+    assert e["speedup_vs_cublas"] > 1.0
+    # mtrand32_new1 N=16 with pivoting fails the reference's own 1e-3 predicate (SURVEY.md 8(d)): it must be reported
+    e = sweep.run_config(16, 1000, "serial_pivot", np.float32, template(inputs, "mtrand32_new1", 16), runs=1)
+    assert e["incorrect_inversions"] == [1000]
