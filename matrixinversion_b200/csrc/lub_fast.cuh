@@ -207,9 +207,12 @@ __device__ __noinline__ void prepass_exact(const T* mimg, int* perm, const int8_
 
 // MI matrices are searched in lock step: their dependency chains (LDS -> REDUX -> VOTE -> SHFL)
 // are independent, so the scheduler overlaps them.
-template <typename T, int N, int MODE, int P, int MS, int MI>
-__device__ __forceinline__ void prepass_warp(const T* __restrict__ img0, int* __restrict__ perm0,
-                                             const int8_t* __restrict__ slot_rank, int lane) {
+// INLINE_EXACT: inline the exact fallback instead of calling it (a call needs the callee's
+// register budget, which a warp that has shrunk its allocation with setmaxnreg does not have).
+// The MI matrices may live anywhere (img[m], perm[m]): a producer warp searches two tiles at once.
+template <typename T, int N, int MODE, int P, int MI, bool INLINE_EXACT = false>
+__device__ __forceinline__ void prepass_warp_ptrs(const T* const (&img)[MI], int* const (&perm)[MI],
+                                                  const int8_t* __restrict__ slot_rank, int lane) {
     using U = typename FpBits<T>::U;
     constexpr unsigned ALL = (N >= 32) ? 0xffffffffu : ((1u << N) - 1u);
     constexpr unsigned REACH = ReachMask<N>::value;
@@ -227,7 +230,7 @@ __device__ __forceinline__ void prepass_warp(const T* __restrict__ img0, int* __
         U v[MI], mx[MI];
         unsigned bal[MI];
 #pragma unroll
-        for (int m = 0; m < MI; ++m) v[m] = FpBits<T>::absbits(img0[m * MS + prow[m] * P + k]);
+        for (int m = 0; m < MI; ++m) v[m] = FpBits<T>::absbits(img[m][prow[m] * P + k]);
 #pragma unroll
         for (int m = 0; m < MI; ++m) mx[m] = warp_max_bits(valid ? v[m] : U(0));
 #pragma unroll
@@ -250,15 +253,27 @@ __device__ __forceinline__ void prepass_warp(const T* __restrict__ img0, int* __
     }
 #pragma unroll
     for (int m = 0; m < MI; ++m)
-        if (lane < N) perm0[m * N + lane] = prow[m];
+        if (lane < N) perm[m][lane] = prow[m];
     if (MODE == kModeParallel) {
 #pragma unroll
         for (int m = 0; m < MI; ++m)
             if (multi[m] != 0u) {  // warp-uniform, rare (needs two equal |values| in one column)
                 __syncwarp();
-                prepass_exact<T, N, MODE, P>(img0 + m * MS, perm0 + m * N, slot_rank, lane);
+                if (INLINE_EXACT) prepass_group<T, N, 32, MODE, P>(img[m], perm[m], slot_rank, lane);
+                else prepass_exact<T, N, MODE, P>(img[m], perm[m], slot_rank, lane);
             }
     }
+}
+
+// MI matrices of one tile: img0 + m * MS, perm0 + m * N
+template <typename T, int N, int MODE, int P, int MS, int MI, bool INLINE_EXACT = false>
+__device__ __forceinline__ void prepass_warp(const T* __restrict__ img0, int* __restrict__ perm0,
+                                             const int8_t* __restrict__ slot_rank, int lane) {
+    const T* img[MI];
+    int* perm[MI];
+#pragma unroll
+    for (int m = 0; m < MI; ++m) { img[m] = img0 + m * MS; perm[m] = perm0 + m * N; }
+    prepass_warp_ptrs<T, N, MODE, P, MI, INLINE_EXACT>(img, perm, slot_rank, lane);
 }
 
 // generic sub-warp pre-pass on a strided image (N <= 16): see pivot_prepass in lub_kernel.cuh

@@ -2,13 +2,13 @@
 // fast kernel for a handful of lane layouts, launched by index so that scripts/tune/run.py can
 // time them side by side on the GPU box.  Build: make -C scripts/tune
 #include <cstdio>
-#include "../../matrixinversion_b200/csrc/lub_v4.cuh"
+#include "../../matrixinversion_b200/csrc/lub_v5.cuh"
 
 using namespace lub;
 
 struct Variant {
     const char* name;
-    int mpw, warp_bytes, header;
+    int mpw, warp_bytes, header;   // warp_bytes < 0: persistent kernel with -warp_bytes threads, header = total smem
     void (*set_attr)(int smem);
     void (*launch)(void*, int*, long long, unsigned, int, int, cudaStream_t);
     int (*occ)(int threads, int smem);
@@ -48,6 +48,24 @@ struct V {
     static Variant make(const char* name) { return Variant{name, L::MPW, L::WARP_BYTES, L::HEADER_BYTES, set_attr, launch, occ}; }
 };
 
+template <typename T, int N, int GR, int GC, int MODE, int NPW, int NCW, int NB, int PRE>
+struct V5 {
+    using L = V5Layout<T, N, GR, GC, MODE, NB>;
+    static void set_attr(int smem) {
+        cudaFuncSetAttribute(lub_v5_kernel<T, N, GR, GC, MODE, NPW, NCW, NB, PRE>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    }
+    static void launch(void* A, int* piv, long long batch, unsigned blocks, int threads, int smem, cudaStream_t s) {
+        lub_v5_kernel<T, N, GR, GC, MODE, NPW, NCW, NB, PRE><<<blocks, threads, smem, s>>>((T*)A, piv, batch);
+    }
+    static int occ(int threads, int smem) {
+        int o = 0;
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, lub_v5_kernel<T, N, GR, GC, MODE, NPW, NCW, NB, PRE>, threads, smem);
+        return o;
+    }
+    static Variant make(const char* name) { return Variant{name, L::MPW, -(NPW + NCW) * 32, L::SMEM_BYTES, set_attr, launch, occ}; }
+};
+#define VAR5(T, N, GR, GC, MODE, NPW, NCW, NB, PRE) V5<T, N, GR, GC, MODE, NPW, NCW, NB, PRE>::make(#T " N=" #N " " #GR "x" #GC " mode" #MODE " p" #NPW " c" #NCW " nb" #NB " opt" #PRE " v5")
+
 #define VAR(T, N, GR, GC, MODE, MINB) V<T, N, GR, GC, MODE, MINB>::make(#T " N=" #N " " #GR "x" #GC " mode" #MODE " minb" #MINB)
 #define VARD(T, N, GR, GC, MODE, MINB, DBG) V<T, N, GR, GC, MODE, MINB, DBG>::make(#T " N=" #N " " #GR "x" #GC " mode" #MODE " minb" #MINB " dbg" #DBG " v4")
 #define VAR3(T, N, GR, GC, MODE, MINB, DBG) V3<T, N, GR, GC, MODE, MINB, DBG>::make(#T " N=" #N " " #GR "x" #GC " mode" #MODE " minb" #MINB " dbg" #DBG " v3")
@@ -60,6 +78,19 @@ extern "C" int tune_count() { return (int)(sizeof(variants) / sizeof(variants[0]
 extern "C" const char* tune_name(int i) { return variants[i].name; }
 extern "C" int tune_launch(int i, void* A, int* piv, long long batch, int threads, void* stream, int* occ_out, int* blocks_out) {
     Variant& v = variants[i];
+    if (v.warp_bytes < 0) {  // persistent producer/consumer kernel: one block per SM
+        threads = -v.warp_bytes;
+        const int smem = v.header;
+        v.set_attr(smem);
+        const int occ = v.occ(threads, smem);
+        if (occ < 1) return -1;
+        const long long ntiles = (batch + v.mpw - 1) / v.mpw;
+        long long blocks = ntiles < 148 ? ntiles : 148;
+        if (occ_out) *occ_out = occ;
+        if (blocks_out) *blocks_out = (int)blocks;
+        v.launch(A, piv, batch, (unsigned)blocks, threads, smem, (cudaStream_t)stream);
+        return cudaGetLastError() == cudaSuccess ? 0 : -2;
+    }
     const int warps = threads / 32;
     const int smem = v.header + warps * v.warp_bytes;
     v.set_attr(smem);
