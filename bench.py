@@ -71,16 +71,21 @@ def cpu_baseline(a, target_s):
 
     dt = np.float32 if a.dtype == "f32" else np.float64
     mode = {"none": 0, "serial": 1, "parallel": 2}[a.mode]
-    cores = O.max_threads()
+    # every host thread we may use -- explicitly, because torch.distributed.run exports
+    # OMP_NUM_THREADS=1 to its workers
+    try:
+        cores = len(os.sched_getaffinity(0))
+    except AttributeError:
+        cores = os.cpu_count() or 1
     rng = np.random.default_rng(32)
     probe = rng.uniform(0, 1, size=(2000, a.n, a.n)).astype(dt)
     t0 = time.perf_counter()
-    O.lu_batched_inplace_timed(probe, mode)
+    O.lu_batched_inplace_timed(probe, mode, cores)
     rate = 2000 / max(time.perf_counter() - t0, 1e-6)
     sample = int(min(a.batch, max(2000, rate * target_s)))
     X = rng.uniform(0, 1, size=(sample, a.n, a.n)).astype(dt)
     t0 = time.perf_counter()
-    used = O.lu_batched_inplace_timed(X, mode)
+    used = O.lu_batched_inplace_timed(X, mode, cores)
     dt_s = time.perf_counter() - t0
     return {"value": sample / dt_s, "unit": UNIT, "cores": used, "kind": "port",
             "sample": "%d distinct uniform(0,1) %dx%d %s matrices, pivot=%s, oracle/lu_oracle.c (C restatement of the "

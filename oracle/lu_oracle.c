@@ -1,6 +1,6 @@
 /*
  * TEST INFRASTRUCTURE ONLY -- see lu_oracle_impl.h.  Builds liblu_oracle.so:
- *   gcc -O2 -fopenmp -ffp-contract=off -shared -fPIC lu_oracle.c -o liblu_oracle.so -lm
+ *   gcc -O3 -fopenmp -ffp-contract=off -shared -fPIC lu_oracle.c -o liblu_oracle.so -lm
  * -ffp-contract=off matters: the FMA / non-FMA choice is made explicitly per call.
  */
 #include <math.h>

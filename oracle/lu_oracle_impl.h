@@ -23,7 +23,8 @@
  *
  * Arithmetic notes.  nvcc contracts `sum += a*b` into an FMA (default -fmad=true),
  * so `use_fma != 0` accumulates with fma(); `use_fma == 0` rounds the product
- * first (what an x86 build of the same C++ would do).  Division is IEEE here; the
+ * first (what an x86 build of the same C++ would do); `use_fma == 2` is the plain expression
+ * `sum + a*b` for the CPU-baseline timing leg (no libm fma() call, no volatile).  Division is IEEE here; the
  * reference sweep builds with --use_fast_math (templated/run.py:47), i.e. an
  * approximate division, which is why value parity is a tolerance and only pivot
  * parity is bit-exact.
@@ -94,6 +95,7 @@ static void ONAME(o_swap_rows)(OT *A, int n, int r1, int r2)
 
 static inline OT ONAME(o_mac)(OT a, OT b, OT sum, int use_fma)
 {
+    if (use_fma == 2) return sum + a * b; /* timing leg: whatever the host compiler makes of it */
     if (use_fma) return OFMA(a, b, sum);
     volatile OT prod = a * b; /* volatile: forbid the host compiler from contracting */
     return sum + prod;
