@@ -4,9 +4,11 @@
 // (parallel_pivot/luBatchedInplace.cu:8-11,118-127) and the NUMTHREADS table of its sweep
 // driver (templated/run.py:201-223).
 #pragma once
+#include <type_traits>
 #include "lub_kernel.cuh"
 #include "lub_fast.cuh"
 #include "lub_v3.cuh"
+#include "lub_v4.cuh"
 
 namespace lub {
 
@@ -64,7 +66,7 @@ constexpr Cfg pick_v3_cfg(int n, int es, bool pivoting) {
     const int chv = (n % epv == 0) ? epv : ((epv == 4 && n % 2 == 0) ? 2 : 1);
     const int ch = pivoting ? 1 : chv;
     const int cpr = n / ch;
-    const int budget = (es == 4) ? 64 : 32;
+    const int budget = (es == 4) ? 64 : 36;  // elements per lane (fp64: 6 x 6 keeps N <= 24 on 16 lanes)
     for (int g = 1; g <= 32; g *= 2) {
         if (g == 2) continue;  // two-lane groups never won a sweep
         int best_cost = 1 << 30;
@@ -126,7 +128,10 @@ cudaError_t launch(void* A, int32_t* piv, long long batch, int threads, cudaStre
     if (dev < 0 || dev >= kMaxDevices) return cudaErrorInvalidDevice;
 
     using VC = V3Cfg<T, N, MODE>;
-    using FL = V3Layout<T, N, VC::GR, VC::GC, MODE>;
+    // fp64 with a multi-lane layout runs the rolled-step kernel (lub_v4.cuh): 5-18 % faster there
+    // (profiles/r01_tune_f64.jsonl); fp32 and one-lane-per-matrix layouts stay on lub_v3.cuh
+    constexpr bool USE_V4 = (sizeof(T) == 8) && (VC::GR * VC::GC > 1);
+    using FL = typename std::conditional<USE_V4, V4Layout<T, N, VC::GR, VC::GC, MODE>, V3Layout<T, N, VC::GR, VC::GC, MODE>>::type;
     using GL = Layout<T, N, AutoCfg<T, N, MODE>::GR, AutoCfg<T, N, MODE>::GC, MODE>;
     // the fast kernel's vector accesses need a 16-byte aligned batch (cudaMalloc gives 256);
     // anything else (a view starting mid-buffer at an odd element) takes the generic kernel
@@ -137,7 +142,8 @@ cudaError_t launch(void* A, int32_t* piv, long long batch, int threads, cudaStre
     KernelCache* c;
     if (fast) {
         smem = FL::HEADER_BYTES + warps * FL::WARP_BYTES; mpw = FL::MPW; g = FL::G; c = &cache_fast[dev];
-        err = prepare(lub_v3_kernel<T, N, VC::GR, VC::GC, MODE, VC::MINB>, *c, dev, threads, smem);
+        if constexpr (USE_V4) err = prepare(lub_v4_kernel<T, N, VC::GR, VC::GC, MODE, VC::MINB, false, 0>, *c, dev, threads, smem);
+        else err = prepare(lub_v3_kernel<T, N, VC::GR, VC::GC, MODE, VC::MINB>, *c, dev, threads, smem);
     } else {
         smem = GL::HEADER_BYTES + warps * GL::WARP_BYTES; mpw = GL::MPW; g = GL::G; c = &cache_gen[dev];
         err = prepare(lub_invert_kernel<T, N, AutoCfg<T, N, MODE>::GR, AutoCfg<T, N, MODE>::GC, MODE>, *c, dev, threads, smem);
@@ -158,10 +164,14 @@ cudaError_t launch(void* A, int32_t* piv, long long batch, int threads, cudaStre
         info->blocks_per_sm = c->blocks_per_sm;
     }
     if (dry_run || batch == 0) return cudaSuccess;
-    if (fast)
-        lub_v3_kernel<T, N, VC::GR, VC::GC, MODE, VC::MINB>
-            <<<(unsigned)blocks, threads, smem, stream>>>(static_cast<T*>(A), piv, batch);
-    else
+    if (fast) {
+        if constexpr (USE_V4)
+            lub_v4_kernel<T, N, VC::GR, VC::GC, MODE, VC::MINB, false, 0>
+                <<<(unsigned)blocks, threads, smem, stream>>>(static_cast<T*>(A), piv, batch);
+        else
+            lub_v3_kernel<T, N, VC::GR, VC::GC, MODE, VC::MINB>
+                <<<(unsigned)blocks, threads, smem, stream>>>(static_cast<T*>(A), piv, batch);
+    } else
         lub_invert_kernel<T, N, AutoCfg<T, N, MODE>::GR, AutoCfg<T, N, MODE>::GC, MODE>
             <<<(unsigned)blocks, threads, smem, stream>>>(static_cast<T*>(A), piv, batch);
     return cudaGetLastError();
