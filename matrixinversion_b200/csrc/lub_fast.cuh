@@ -1,22 +1,11 @@
-// lub_fast.cuh -- second-generation hot-path kernel (same result as lub_kernel.cuh, see the
-// algorithm notes there) built around what Nsight Compute showed on B200 for the first one:
-// the LSU / shared-memory pipe, not HBM or the FMA pipe, was the limiter (74 % busy, 63 % of
-// its wavefronts bank-conflict replays; profiles/r01_v1_n32_f32_parallel.md).
+// lub_fast.cuh -- helpers shared by the v3 / v4 / v5 kernels: padded 128-bit image layout and
+// copies (pivot_mode none), vector load/store helpers, lane-dependent select / predicated move
+// wrappers, and the pivot pre-pass (warp-wide REDUX search + exact group search).
 //
-//   * the shared-memory image of a tile keeps 16-byte vector access but pads every row (and
-//     every matrix) by a few words, chosen at compile time so that a column walk (pivot
-//     search) and the 2-D register load no longer map rows onto the same banks;
-//   * per-step pivot row / multiplier exchange goes through two small double-buffered
-//     shared-memory vectors written by the owning lanes with 128-bit stores and read back
-//     with 128-bit broadcast loads (about 10 LSU instructions per step per tile instead of
-//     21 shuffles), one __syncwarp per step, no block barrier anywhere;
-//   * pivot pre-pass for N > 16 runs one matrix per warp with lane = row position:
-//     column value -> REDUX max -> ballot -> first set bit, one shuffle to swap two lanes'
-//     row ids.  find_pivot_parallel's tree (parallel_pivot/luBatchedInplace.cuh:12-44) is
-//     reproduced by a per-step compile-time mask of the slots the tree can reach plus a
-//     rank tie-break executed only when two candidates hold the same maximal value;
-//   * multipliers are produced by the lanes owning column k directly into consecutive
-//     registers (no gather moves), and FFMA2 takes them as a scalar-broadcast operand.
+// History: this file used to hold the second-generation kernel (shared-memory mailbox exchange).
+// Nsight Compute showed a 128-bit LDS/STS costs four wavefronts even as a broadcast and that
+// predicated owner stores pay per quarter-warp, i.e. a mailbox costs twice the wavefronts of
+// shuffles (profiles/r01_prof_v2_n32.md); the kernel was replaced by lub_v3.cuh and removed.
 #pragma once
 #include "lub_kernel.cuh"
 
@@ -56,36 +45,6 @@ constexpr int pick_mat_pad() {  // elements; multiple of 16 bytes; spreads the t
     return 0;
 }
 
-template <typename T, int N, int GR, int GC, int MODE>
-struct FastLayout {
-    static constexpr int ES = sizeof(T);
-    static constexpr int EPV = 16 / ES;
-    // widest power-of-two chunk (elements) that divides every row: vector width of all row accesses
-    static constexpr int CH = (N % EPV == 0) ? EPV : ((EPV == 4 && N % 2 == 0) ? 2 : 1);
-    static constexpr int G = GR * GC;
-    static_assert(G >= 1 && G <= 32 && (32 % G) == 0, "G must divide 32");
-    static constexpr int MPW = 32 / G;
-    static constexpr int CPR = N / CH;              // chunks per row
-    static constexpr int CPL = cdiv_(CPR, GC);      // chunks per lane (cyclic over GC)
-    static constexpr int LC = CPL * CH;
-    static constexpr int LR = cdiv_(N, GR);         // rows per lane (cyclic over GR)
-    static constexpr bool ROWVEC = (CH == EPV);     // rows are whole 16-byte chunks -> padded image
-    static constexpr int RPAD = ROWVEC ? pick_row_pad<T, N>() : 0;
-    static constexpr int P = N + RPAD;              // image row stride (elements)
-    static constexpr int MPAD = ROWVEC ? pick_mat_pad<T, N, P, MPW>() : 0;
-    static constexpr int MS = N * P + MPAD;         // image matrix stride (elements)
-    static constexpr int LRP = roundup_(LR, EPV);   // multiplier vector per lane-row, 16-byte padded
-    static constexpr int XROW = roundup_(N, EPV);
-    static constexpr int XCOL = GR * LRP;
-    static constexpr int XB = XROW + XCOL;          // one exchange buffer (elements)
-    static constexpr int IMG_BYTES = roundup_(MPW * MS * ES, 16) + 16;
-    static constexpr int PERM_BYTES = (MODE != kModeNone) ? roundup_(MPW * N * 4, 16) : 0;
-    static constexpr int XBUF_BYTES = (G > 1) ? MPW * 2 * XB * ES : 0;
-    static constexpr int WARP_BYTES = IMG_BYTES + PERM_BYTES + XBUF_BYTES;
-    static constexpr int HEADER_BYTES = 64;
-    // 16-byte units, for the padded copy
-    static constexpr int CPR16 = N * ES / 16, RPAD16 = RPAD * ES / 16, MPAD16 = MPAD * ES / 16;
-};
 
 // Lane-dependent selects are written as PTX selp so that the compiler keeps them as one
 // FSEL each: given a C++ ?: it if-converts the whole rank-1 update into two divergent copies
@@ -310,210 +269,6 @@ __device__ __forceinline__ void prepass_group(const T* __restrict__ mimg, int* _
             const int tmp = perm[k];
             perm[k] = perm[p];
             perm[p] = tmp;
-        }
-        __syncwarp();
-    }
-}
-
-// ---- the kernel -------------------------------------------------------------------------------
-
-template <typename T, int N, int GR, int GC, int MODE, int MINB = 1>
-__global__ void __launch_bounds__(kMaxThreads, MINB)
-lub_fast_kernel(T* __restrict__ A, int32_t* __restrict__ piv, long long batch) {
-    using L = FastLayout<T, N, GR, GC, MODE>;
-    constexpr int G = L::G, MPW = L::MPW, LR = L::LR, LC = L::LC, CH = L::CH, CPL = L::CPL, CPR = L::CPR;
-    constexpr int P = L::P, MS = L::MS, EPV = L::EPV, LRP = L::LRP;
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-
-    const int lane = threadIdx.x & 31;
-    const int warp = threadIdx.x >> 5;
-    const int nwarps = blockDim.x >> 5;
-    int8_t* slot_rank = reinterpret_cast<int8_t*>(smem_raw);
-    unsigned char* wbase = smem_raw + L::HEADER_BYTES + (size_t)warp * L::WARP_BYTES;
-    int* perm_all = reinterpret_cast<int*>(wbase + L::IMG_BYTES);
-    T* xbuf_all = reinterpret_cast<T*>(wbase + L::IMG_BYTES + L::PERM_BYTES);
-
-    if (MODE == kModeParallel) {
-        if (threadIdx.x < N) slot_rank[threadIdx.x] = (int8_t)tree_slot_rank(threadIdx.x, N);
-        __syncthreads();
-    }
-
-    const int g = lane % G;
-    const int ml = lane / G;
-    const int gr = g / GC;
-    const int gc = g % GC;
-    const int grp_base = ml * G;
-    T* xb0 = xbuf_all + ml * (2 * L::XB);
-
-    const long long ntiles = (batch + MPW - 1) / MPW;
-#pragma unroll 1
-    for (long long tile = (long long)blockIdx.x * nwarps + warp; tile < ntiles;
-         tile += (long long)gridDim.x * nwarps) {
-        const long long first = tile * MPW;
-        const int nm = (batch - first < MPW) ? (int)(batch - first) : MPW;
-        T* gspan = A + first * (long long)(N * N);
-        T* img;
-        if constexpr (L::ROWVEC) {
-            img = reinterpret_cast<T*>(wbase);
-            copy_in_padded<T, L, N>(wbase, gspan, nm * N * L::CPR16, lane);
-        } else {
-            const unsigned mis = (unsigned)(reinterpret_cast<uintptr_t>(gspan) & 15u);
-            img = reinterpret_cast<T*>(wbase + mis);
-            copy_in<T>(img, gspan, nm * N * N, MPW * N * N, lane);
-        }
-        __syncwarp();
-
-        T* mimg = img + ml * MS;
-        int* perm = perm_all + ml * N;
-        if (MODE != kModeNone) {
-            if (N > 16) {
-                constexpr int MI = (MPW < 4) ? MPW : 4;
-#pragma unroll 1
-                for (int m = 0; m < MPW; m += MI)
-                    prepass_warp<T, N, MODE, P, MS, MI>(img + m * MS, perm_all + m * N, slot_rank, lane);
-            } else {
-                prepass_group<T, N, G, MODE, P>(mimg, perm, slot_rank, g);
-            }
-            __syncwarp();
-        }
-
-        // ---- registers <- image: rows permuted, LR x LC block per lane ---------------------
-        T a[LR][LC];
-#pragma unroll
-        for (int li = 0; li < LR; ++li) {
-            const int i = li * GR + gr;
-            const bool rok = (li * GR + GR - 1 < N) || (i < N);
-            int prow = i;
-            if (MODE != kModeNone) prow = rok ? perm[i] : 0;
-            const T* rowp = mimg + prow * P;
-#pragma unroll
-            for (int q = 0; q < CPL; ++q) {
-                const int cq = q * GC + gc;
-                const bool ok = rok && ((q * GC + GC - 1 < CPR) || (cq < CPR));
-                if (ok) {
-                    ld_vec<T, CH>(rowp + cq * CH, &a[li][q * CH]);
-                } else {
-#pragma unroll
-                    for (int w = 0; w < CH; ++w) a[li][q * CH + w] = T(0);
-                }
-            }
-        }
-
-        // ---- Gauss-Jordan with deferred row scaling ------------------------------------------
-        T dinv[LR];
-#pragma unroll
-        for (int li = 0; li < LR; ++li) dinv[li] = T(0);
-#pragma unroll
-        for (int k = 0; k < N; ++k) {
-            const int gro = k % GR, lk = k / GR;
-            const int cj = k / CH, gco = cj % GC, ck = (cj / GC) * CH + (k % CH);
-            const bool own_row = (GR == 1) || (gr == gro);
-            const bool own_col = (GC == 1) || (gc == gco);
-            T* rowbuf = xb0 + (k & 1) * L::XB;
-            T* colbuf = rowbuf + L::XROW;
-            T r[LC], nf[LRP];
-
-            if (GR > 1) {  // owners of row k publish their pieces
-                if (own_row) {
-#pragma unroll
-                    for (int q = 0; q < CPL; ++q) {
-                        const int cq = q * GC + gc;
-                        if ((q * GC + GC - 1 < CPR) || (cq < CPR)) st_vec<T, CH>(rowbuf + cq * CH, &a[lk][q * CH]);
-                    }
-                }
-            }
-            T rinv;
-            if (GC > 1) {  // owners of column k compute the multipliers and publish them
-                const T pv = shfl_t(a[lk][ck], grp_base + gro * GC + gco);
-                rinv = rcp_t(pv);
-#pragma unroll
-                for (int li = 0; li < LRP; ++li) nf[li] = (li < LR) ? -(a[li < LR ? li : 0][ck] * rinv) : T(0);
-                nf[lk] = sel_t(own_row, T(0), nf[lk]);
-                if (own_col) {
-#pragma unroll
-                    for (int v = 0; v < LRP; v += EPV) st_vec<T, EPV>(colbuf + gr * LRP + v, &nf[v]);
-                }
-            }
-            if (G > 1) __syncwarp();
-            if (GR > 1) {
-#pragma unroll
-                for (int q = 0; q < CPL; ++q) {
-                    const int cq = q * GC + gc;
-                    if ((q * GC + GC - 1 < CPR) || (cq < CPR)) {
-                        ld_vec<T, CH>(rowbuf + cq * CH, &r[q * CH]);
-                    } else {
-#pragma unroll
-                        for (int w = 0; w < CH; ++w) r[q * CH + w] = T(0);
-                    }
-                }
-            } else {
-#pragma unroll
-                for (int lj = 0; lj < LC; ++lj) r[lj] = a[lk][lj];
-            }
-            if (GC > 1) {
-#pragma unroll
-                for (int v = 0; v < LRP; v += EPV) ld_vec<T, EPV>(colbuf + gr * LRP + v, &nf[v]);
-            } else {
-                rinv = rcp_t(r[ck]);  // every lane holds whole rows: column k is local
-#pragma unroll
-                for (int li = 0; li < LR; ++li) nf[li] = -(a[li][ck] * rinv);
-                nf[lk] = sel_t(own_row, T(0), nf[lk]);
-            }
-            // slot k now belongs to column k of the augmented identity
-            r[ck] = sel_t(own_col, T(1), r[ck]);
-            const T diag = sel_t(own_row, T(1), T(0));
-#pragma unroll
-            for (int li = 0; li < LR; ++li) a[li][ck] = sel_t(own_col, (li == lk) ? diag : T(0), a[li][ck]);
-#pragma unroll
-            for (int li = 0; li < LR; ++li) row_update<LC>(a[li], r, nf[li]);
-            dinv[lk] = sel_t(own_row, rinv, dinv[lk]);
-        }
-
-        // ---- scale by 1/pivot, undo the row permutation as a column scatter -------------------
-        __syncwarp();
-#pragma unroll
-        for (int li = 0; li < LR; ++li) {
-#pragma unroll
-            for (int lj = 0; lj < LC; ++lj) a[li][lj] *= dinv[li];
-        }
-        if (MODE == kModeNone) {
-#pragma unroll
-            for (int li = 0; li < LR; ++li) {
-                const int i = li * GR + gr;
-                const bool rok = (li * GR + GR - 1 < N) || (i < N);
-#pragma unroll
-                for (int q = 0; q < CPL; ++q) {
-                    const int cq = q * GC + gc;
-                    if (rok && ((q * GC + GC - 1 < CPR) || (cq < CPR))) st_vec<T, CH>(mimg + i * P + cq * CH, &a[li][q * CH]);
-                }
-            }
-        } else {
-            int pcol[LC];
-#pragma unroll
-            for (int q = 0; q < CPL; ++q) {
-                const int cq = q * GC + gc;
-                const bool ok = (q * GC + GC - 1 < CPR) || (cq < CPR);
-#pragma unroll
-                for (int w = 0; w < CH; ++w) pcol[q * CH + w] = ok ? perm[cq * CH + w] : -1;
-            }
-#pragma unroll
-            for (int li = 0; li < LR; ++li) {
-                const int i = li * GR + gr;
-                const bool rok = (li * GR + GR - 1 < N) || (i < N);
-#pragma unroll
-                for (int lj = 0; lj < LC; ++lj)
-                    if (rok && pcol[lj] >= 0) mimg[i * P + pcol[lj]] = a[li][lj];
-            }
-        }
-        __syncwarp();
-        if constexpr (L::ROWVEC) copy_out_padded<T, L, N>(gspan, wbase, nm * N * L::CPR16, lane);
-        else copy_out<T>(gspan, img, nm * N * N, lane);
-        int32_t* pivp = piv;
-        asm volatile("" : "+l"(pivp));  // opaque: keeps the compiler from cloning the whole tile loop on piv == NULL
-        if (pivp != nullptr) {
-            int32_t* pdst = pivp + first * N;
-            for (int e = lane; e < nm * N; e += 32)
-                pdst[e] = (MODE != kModeNone) ? perm_all[e] : (e % N);
         }
         __syncwarp();
     }

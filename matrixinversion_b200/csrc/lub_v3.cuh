@@ -1,5 +1,5 @@
-// lub_v3.cuh -- third-generation hot-path kernel.  Same algorithm and results as
-// lub_kernel.cuh / lub_fast.cuh; the data movement is re-planned around the cost model that
+// lub_v3.cuh -- third-generation hot-path kernel (the one the library launches for fp32).  Same
+// algorithm and results as lub_kernel.cuh; the data movement is re-planned around the cost model that
 // Nsight Compute measurements on B200 established (profiles/r01_*.md):
 //
 //   * the shared-memory crossbar delivers one 32-bit word per lane per cycle per SM, whatever
@@ -12,7 +12,7 @@
 //   * pivoting modes use an element-granular image with an ODD row stride, so the pivot
 //     search's column walk and the permuted row gather are bank-conflict free; the price is
 //     scalar instead of 128-bit shared-memory instructions, which cost the same wavefronts.
-//   * pivot_mode none keeps the 128-bit padded image of lub_fast.cuh.
+//   * pivot_mode none keeps a 128-bit padded image (helpers in lub_fast.cuh).
 #pragma once
 #include "lub_fast.cuh"
 

@@ -309,3 +309,40 @@ def test_sweep_driver_records_correctness(tmp_path, inputs):
     assert e["incorrect_inversions"] == ([1000] if bad else [])
     Xbad = X.copy(); Xbad[0, 0, 0] += 1.0
     assert lub.verify_inv(T16[None], Xbad)[1] == 1
+
+
+def test_generic_kernel_for_unaligned_even_n():
+    """A batch whose base pointer is element-aligned but not 16-byte aligned (a view one
+    element into a flat buffer) takes the generic fallback kernel (csrc/lub_kernel.cuh);
+    results must equal the aligned launch bit for bit, and the bytes around the view stay."""
+    for n, dtype in ((6, np.float32), (20, np.float32), (32, np.float32), (8, np.float64), (32, np.float64)):
+        A = synthetic(n, 77, dtype)
+        flat = torch.full((A.size + 8,), 123.0, dtype=torch.float32 if dtype == np.float32 else torch.float64, device="cuda")
+        off = 1 if dtype == np.float32 else 1   # 4 or 8 bytes past a 256-byte aligned allocation
+        view = flat[off:off + A.size].view(77, n, n)
+        view.copy_(torch.from_numpy(A))
+        assert view.data_ptr() % 16 != 0
+        piv = torch.zeros((77, n), dtype=torch.int32, device="cuda")
+        for mode in (0, 2):
+            view.copy_(torch.from_numpy(A if mode else A + n * np.eye(n, dtype=dtype)))
+            lub.lu_batched_inplace(view, piv, mode)
+            X, p = gpu_invert(A if mode else A + n * np.eye(n, dtype=dtype), mode)
+            assert np.array_equal(piv.cpu().numpy(), p), (n, dtype, mode)
+            np.testing.assert_allclose(view.cpu().numpy(), X, rtol=1e-4 if dtype == np.float32 else 1e-11, atol=0)
+        assert flat[0].item() == 123.0 and bool((flat[off + A.size:] == 123.0).all())
+
+
+def test_geometry_timing_and_device_info():
+    info = lub.device_info()
+    assert info["sm_count"] >= 100 and info["cc_major"] >= 10
+    g = lub.geometry(32, 1_000_000, "parallel", np.float32)
+    assert g.threads_per_block % 32 == 0 and 32 % g.threads_per_matrix == 0 and g.num_blocks >= info["sm_count"]
+    assert g.matrices_per_block == (g.threads_per_block // 32) * (32 // g.threads_per_matrix)
+    A = torch.from_numpy(synthetic(16, 5000, np.float32)).cuda()
+    assert lub.last_kernel_ms() < 0          # nothing timed yet on this thread
+    lub.enable_timing(True)
+    try:
+        lub.lu_batched_inplace(A, None, "serial")
+        assert 0 < lub.last_kernel_ms() < 100
+    finally:
+        lub.enable_timing(False)
