@@ -204,3 +204,37 @@ def test_tree_rank_rule_equals_literal_tree():
                 _, po, so = O.lu_batched(A[None], mode, lu_only=True, want_steps=True)
                 p, s = rule(A, mode)
                 assert s == so[0].tolist() and p == po[0].tolist(), (n, mode, trial)
+
+
+def test_oracle_matches_reference_gpu_kernel_goldens(inputs):
+    """tests/golden/golden_gpu_ref.npz = outputs of the reference's OWN CUDA kernels run on a
+    B200 (make_golden_gpu.py).  The oracle must reproduce their permutation vectors exactly --
+    this pins the restated find_pivot_parallel tree, dropped slots included (N = 17, 18, 20,
+    24, 27, 31), to the real kernel -- and their inverses to rounding (the kernels were built
+    with --use_fast_math, the oracle divides exactly)."""
+    import os
+    from conftest import GOLDEN
+    g = np.load(os.path.join(GOLDEN, "golden_gpu_ref.npz"))
+    n_piv = n_val = 0
+    for key in g.files:
+        kind, name, suf, mode, n = key.split("/")
+        mode, n = int(mode), int(n)
+        dt = np.float32 if suf == "f32" else np.float64
+        A = template(inputs, name, n, dt)
+        with np.errstate(all="ignore"):
+            X, perm = O.lu_batched(A[None], mode)
+        if kind == "piv":
+            assert perm[0].tolist() == g[key].tolist(), key
+            n_piv += 1
+        else:
+            ref = g[key]
+            if not np.isfinite(ref).all():
+                continue
+            eps = 2.0 ** -23 if dt == np.float32 else 2.0 ** -52
+            kappa = np.linalg.cond(A.astype(np.float64))
+            Xt = np.linalg.inv(A.astype(np.float64))
+            err_ref = np.abs(ref - Xt).max()
+            tol = max(16 * n * eps * kappa * np.abs(Xt).max(), 8 * err_ref)
+            assert np.abs(X[0].astype(np.float64) - ref).max() <= tol, key
+            n_val += 1
+    assert n_piv >= 150 and n_val >= 200
