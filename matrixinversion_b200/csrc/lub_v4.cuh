@@ -39,11 +39,13 @@ constexpr int load_conflict(int p, int ms, int gr_n, int gc_n, int ew) {
 
 struct Strides { int p, ms; };
 
-constexpr Strides pick_strides(int n, int gr, int gc, int ew) {
+// odd_only: the pivot search walks columns (row stride must be odd to be conflict-free); without
+// pivoting any stride will do and a conflict-free register load usually exists with an even one
+constexpr Strides pick_strides(int n, int gr, int gc, int ew, bool odd_only) {
     const int slots = 32 / ew;
     int best = 1 << 30;
     Strides s{n | 1, n * (n | 1)};
-    for (int p = n | 1; p < n + 2 * slots; p += 2) {
+    for (int p = odd_only ? (n | 1) : n; p < n + 2 * slots; p += odd_only ? 2 : 1) {
         for (int pad = 0; pad < slots; ++pad) {
             const int ms = n * p + pad;
             const int c = load_conflict(p, ms, gr, gc, ew) * 4096 + (p - n) * 64 + pad;
@@ -64,7 +66,7 @@ struct V4Layout {
     static constexpr int LR = cdiv_(N, GR);  // local rows:    i = li * GR + gr
     static constexpr int LC = cdiv_(N, GC);  // local columns: j = lj * GC + gc
     static constexpr int GM = GR < GC ? GR : GC;  // steps that share one code body
-    static constexpr Strides S = pick_strides(N, GR, GC, EW);
+    static constexpr Strides S = pick_strides(N, GR, GC, EW, MODE != kModeNone);
     static constexpr int P = S.p, MS = S.ms, MPAD = MS - N * P;
     static constexpr bool ALIGNED = ((MPW * N * N * ES) % 16) == 0;
     static constexpr int IMG_BYTES = roundup_(MPW * MS * ES, 16) + 16;
@@ -190,7 +192,7 @@ lub_v4_kernel(T* __restrict__ A, int32_t* __restrict__ piv, long long batch) {
             const int lk = (kb * GM) / GR;          // local row of rows kb*GM .. kb*GM+GM-1
             const int ck = (kb * GM) / GC;          // local column of those columns
             const int gro0 = (kb * GM) % GR, gco0 = (kb * GM) % GC;
-#pragma unroll ((DBG & 16) ? GM : 1)
+#pragma unroll ((DBG & 16) ? GM : ((DBG & 32) ? 2 : 1))
             for (int s = 0; s < GM; ++s) {
                 if (kb * GM + s >= NSTEP) break;
                 const int gro = gro0 + s, gco = gco0 + s;   // run-time owners of pivot row / column
@@ -214,8 +216,15 @@ lub_v4_kernel(T* __restrict__ A, int32_t* __restrict__ piv, long long batch) {
 #pragma unroll
                 for (int li = 0; li < LR; ++li) nf[li] = -(c[li] * rinv);
                 nf[lk] = sel_t(own_row, T(0), nf[lk]);
+                if (DBG & 64) {  // tuning: clear column k with selects (ALU pipe) and use the plain update
 #pragma unroll
-                for (int li = 0; li < LR; ++li) row_update_masked<LC>(a[li], r, nf[li], ck, zmask);
+                    for (int li = 0; li < LR; ++li) a[li][ck] = sel_t(own_col, T(0), a[li][ck]);
+#pragma unroll
+                    for (int li = 0; li < LR; ++li) row_update<LC>(a[li], r, nf[li]);
+                } else {
+#pragma unroll
+                    for (int li = 0; li < LR; ++li) row_update_masked<LC>(a[li], r, nf[li], ck, zmask);
+                }
                 // the pivot row's own slot-k entry is the 1 of the identity column
                 a[lk][ck] = sel_t(own_row && own_col, T(1), a[lk][ck]);
                 dinv[lk] = sel_t(own_row, rinv, dinv[lk]);
