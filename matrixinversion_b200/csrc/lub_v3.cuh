@@ -18,6 +18,35 @@
 
 namespace lub {
 
+// worst bank multiplicity of one warp-wide scalar access where lane (ml, gr, gc) touches element
+// offset ml*ms + gr*p + gc*cm; ew = words per element (64-bit elements are served per half-warp)
+constexpr int lane_conflict(int p, int ms, int gr_n, int gc_n, int cm, int ew) {
+    const int g = gr_n * gc_n, slots = 32 / ew;
+    int worst = 0;
+    for (int half = 0; half < ew; ++half) {
+        int cnt[32] = {};
+        for (int lane = half * (32 / ew); lane < (half + 1) * (32 / ew); ++lane) {
+            const int ml = lane / g, gg = lane % g, gr = gg / gc_n, gc = gg % gc_n;
+            const int s = (ml * ms + gr * p + gc * cm) % slots;
+            if (++cnt[s] > worst) worst = cnt[s];
+        }
+    }
+    return worst;
+}
+struct ScStrides { int p, pad; };
+constexpr ScStrides pick_sc_strides(int n, int gr, int gc, int cm, int ew) {
+    const int slots = 32 / ew;
+    int best = 1 << 30;
+    ScStrides s{n | 1, 0};
+    for (int p = n | 1; p <= (n | 1) + 8; p += 2) {
+        for (int pad = 0; pad < slots; ++pad) {
+            const int c = lane_conflict(p, n * p + pad, gr, gc, cm, ew) * 4096 + (p - n) * 64 + pad;
+            if (c < best) { best = c; s = ScStrides{p, pad}; }
+        }
+    }
+    return s;
+}
+
 template <typename T, int N, int GR, int GC, int MODE>
 struct V3Layout {
     static constexpr int ES = sizeof(T);
@@ -34,11 +63,14 @@ struct V3Layout {
     static constexpr int LC = CPL * CH;
     static constexpr int LR = cdiv_(N, GR);     // rows per lane, cyclic over GR
     static constexpr bool ROWVEC = !SC && (CH == EPV);
-    static constexpr int P = SC ? (N | 1) : (ROWVEC ? N + pick_row_pad<T, N>() : N);
     static constexpr int SLOTS = 32 / EW;
-    static constexpr int SC_TARGET = (SLOTS / MPW) > 0 ? (SLOTS / MPW) : 1;
-    static constexpr int MPAD = SC ? ((MPW == 1) ? 0 : ((SC_TARGET - (N * P) % SLOTS + SLOTS) % SLOTS))
-                                   : (ROWVEC ? pick_mat_pad<T, N, P, MPW>() : 0);
+    // element-granular image: odd row stride P (conflict-free column walks for the pivot search)
+    // and matrix padding, searched together so that the register load -- lane (ml, gr, gc) reads
+    // element ml*MS + gr*P + gc*LC -- spreads the warp over as many banks as possible
+    // (2-way conflicts there cost ~11 % of the LSU time, profiles/r01_prof_headline_*.md)
+    static constexpr ScStrides SCS = pick_sc_strides(N, GR, GC, LC, EW);
+    static constexpr int P = SC ? SCS.p : (ROWVEC ? N + pick_row_pad<T, N>() : N);
+    static constexpr int MPAD = SC ? SCS.pad : (ROWVEC ? pick_mat_pad<T, N, P, MPW>() : 0);
     static constexpr int MS = N * P + MPAD;
     static constexpr bool ALIGNED = ((MPW * N * N * ES) % 16) == 0;  // every tile span starts on 16 bytes
     static constexpr int IMG_BYTES = roundup_(MPW * MS * ES, 16) + 16;
