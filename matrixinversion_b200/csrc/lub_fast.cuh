@@ -164,6 +164,56 @@ __device__ __noinline__ void prepass_exact(const T* mimg, int* perm, const int8_
     prepass_group<T, N, 32, MODE, P>(mimg, perm, slot_rank, lane);
 }
 
+#ifndef LUB_ROWWISE_PREPASS
+#define LUB_ROWWISE_PREPASS 1
+#endif
+constexpr bool kRowwisePrepass = LUB_ROWWISE_PREPASS != 0;
+
+// Row-wise search (lane = ORIGINAL row).  Usable whenever the candidate set of step k is simply
+// "every row not picked yet" -- serial mode, and parallel mode when the reference tree reaches all
+// of its slots (N a power of two): find_pivot looks at un-eliminated entries only
+// (serial_pivot/luBatchedInplace.cuh:24-41, parallel_pivot/...cuh:25-68), so a row's key for column k
+// never changes and row positions matter for tie-breaks alone.  Each step is LDS (static address)
+// -> key -> REDUX.MAX -> compare -> two selects: no ballot, no shuffle, and a dependency chain a
+// third as long as the position-wise search below.  The row picked at step k ends at position k for
+// good, so lane r just remembers the step at which it was picked (= its final position).  A step with
+// two equal maxima retires two lanes at once; then the survivors do not add up to one at the end
+// and the matrix is redone by the exact search (rare: needs equal |values| in one column).
+template <typename T, int N, int MODE, int P, int MI, bool INLINE_EXACT>
+__device__ __forceinline__ void prepass_rowwise(const T* const (&img)[MI], int* const (&perm)[MI],
+                                                const int8_t* __restrict__ slot_rank, int lane) {
+    using U = typename FpBits<T>::U;
+    const int roff = ((lane < N) ? lane : 0) * P;
+    U alive[MI];
+    int when[MI];
+#pragma unroll
+    for (int m = 0; m < MI; ++m) { alive[m] = (lane < N) ? ~U(0) : U(0); when[m] = N - 1; }
+#pragma unroll
+    for (int k = 0; k < N - 1; ++k) {
+        U key[MI], mx[MI];
+#pragma unroll
+        for (int m = 0; m < MI; ++m) key[m] = ((FpBits<T>::absbits(img[m][roff + k]) << 1) | U(1)) & alive[m];
+#pragma unroll
+        for (int m = 0; m < MI; ++m) mx[m] = warp_max_bits(key[m]);
+#pragma unroll
+        for (int m = 0; m < MI; ++m) {
+            const bool hit = key[m] == mx[m];
+            when[m] = hit ? k : when[m];
+            alive[m] = hit ? U(0) : alive[m];
+        }
+    }
+#pragma unroll
+    for (int m = 0; m < MI; ++m) {
+        const bool ok = __popc(__ballot_sync(0xffffffffu, alive[m] != U(0))) == 1;  // warp-uniform
+        if (ok) {
+            if (lane < N) perm[m][when[m]] = lane;
+        } else {
+            if (INLINE_EXACT) prepass_group<T, N, 32, MODE, P>(img[m], perm[m], slot_rank, lane);
+            else prepass_exact<T, N, MODE, P>(img[m], perm[m], slot_rank, lane);
+        }
+    }
+}
+
 // MI matrices are searched in lock step: their dependency chains (LDS -> REDUX -> VOTE -> SHFL)
 // are independent, so the scheduler overlaps them.
 // INLINE_EXACT: inline the exact fallback instead of calling it (a call needs the callee's
@@ -175,6 +225,9 @@ __device__ __forceinline__ void prepass_warp_ptrs(const T* const (&img)[MI], int
     using U = typename FpBits<T>::U;
     constexpr unsigned ALL = (N >= 32) ? 0xffffffffu : ((1u << N) - 1u);
     constexpr unsigned REACH = ReachMask<N>::value;
+    if constexpr (kRowwisePrepass && (MODE == kModeSerial || (REACH & (ALL >> 1)) == (ALL >> 1))) {
+        prepass_rowwise<T, N, MODE, P, MI, INLINE_EXACT>(img, perm, slot_rank, lane);
+    } else {
     int prow[MI];  // original row sitting at position `lane`
     unsigned multi[MI];
 #pragma unroll
@@ -221,6 +274,7 @@ __device__ __forceinline__ void prepass_warp_ptrs(const T* const (&img)[MI], int
                 if (INLINE_EXACT) prepass_group<T, N, 32, MODE, P>(img[m], perm[m], slot_rank, lane);
                 else prepass_exact<T, N, MODE, P>(img[m], perm[m], slot_rank, lane);
             }
+    }
     }
 }
 
