@@ -168,6 +168,10 @@ __device__ __noinline__ void prepass_exact(const T* mimg, int* perm, const int8_
 #define LUB_ROWWISE_PREPASS 1
 #endif
 constexpr bool kRowwisePrepass = LUB_ROWWISE_PREPASS != 0;
+constexpr bool rowwise_prepass_ok(int n, int mode) {
+    const unsigned all = (n >= 32) ? 0xffffffffu : ((1u << n) - 1u);
+    return kRowwisePrepass && (mode == kModeSerial || (reach_mask_of(n) & (all >> 1)) == (all >> 1));
+}
 
 // Row-wise search (lane = ORIGINAL row).  Usable whenever the candidate set of step k is simply
 // "every row not picked yet" -- serial mode, and parallel mode when the reference tree reaches all
@@ -179,7 +183,9 @@ constexpr bool kRowwisePrepass = LUB_ROWWISE_PREPASS != 0;
 // good, so lane r just remembers the step at which it was picked (= its final position).  A step with
 // two equal maxima retires two lanes at once; then the survivors do not add up to one at the end
 // and the matrix is redone by the exact search (rare: needs equal |values| in one column).
-template <typename T, int N, int MODE, int P, int MI, bool INLINE_EXACT>
+template <int N, int MODE> struct RowwiseOk { static constexpr bool value = rowwise_prepass_ok(N, MODE); };
+
+template <typename T, int N, int MODE, int P, int MI, bool INLINE_EXACT, bool VEC = false>
 __device__ __forceinline__ void prepass_rowwise(const T* const (&img)[MI], int* const (&perm)[MI],
                                                 const int8_t* __restrict__ slot_rank, int lane) {
     using U = typename FpBits<T>::U;
@@ -188,11 +194,20 @@ __device__ __forceinline__ void prepass_rowwise(const T* const (&img)[MI], int* 
     int when[MI];
 #pragma unroll
     for (int m = 0; m < MI; ++m) { alive[m] = (lane < N) ? ~U(0) : U(0); when[m] = N - 1; }
+    constexpr int EPV = 16 / (int)sizeof(T);
+    T x[MI][EPV];
 #pragma unroll
     for (int k = 0; k < N - 1; ++k) {
         U key[MI], mx[MI];
+        if (VEC && (k % EPV) == 0) {  // 16-byte image: one vector load feeds EPV steps
 #pragma unroll
-        for (int m = 0; m < MI; ++m) key[m] = ((FpBits<T>::absbits(img[m][roff + k]) << 1) | U(1)) & alive[m];
+            for (int m = 0; m < MI; ++m) ld_vec<T, EPV>(img[m] + roff + k, x[m]);
+        }
+#pragma unroll
+        for (int m = 0; m < MI; ++m) {
+            const T xv = VEC ? x[m][k % EPV] : img[m][roff + k];
+            key[m] = ((FpBits<T>::absbits(xv) << 1) | U(1)) & alive[m];
+        }
 #pragma unroll
         for (int m = 0; m < MI; ++m) mx[m] = warp_max_bits(key[m]);
 #pragma unroll
@@ -219,14 +234,14 @@ __device__ __forceinline__ void prepass_rowwise(const T* const (&img)[MI], int* 
 // INLINE_EXACT: inline the exact fallback instead of calling it (a call needs the callee's
 // register budget, which a warp that has shrunk its allocation with setmaxnreg does not have).
 // The MI matrices may live anywhere (img[m], perm[m]): a producer warp searches two tiles at once.
-template <typename T, int N, int MODE, int P, int MI, bool INLINE_EXACT = false>
+template <typename T, int N, int MODE, int P, int MI, bool INLINE_EXACT = false, bool VEC = false>
 __device__ __forceinline__ void prepass_warp_ptrs(const T* const (&img)[MI], int* const (&perm)[MI],
                                                   const int8_t* __restrict__ slot_rank, int lane) {
     using U = typename FpBits<T>::U;
     constexpr unsigned ALL = (N >= 32) ? 0xffffffffu : ((1u << N) - 1u);
     constexpr unsigned REACH = ReachMask<N>::value;
-    if constexpr (kRowwisePrepass && (MODE == kModeSerial || (REACH & (ALL >> 1)) == (ALL >> 1))) {
-        prepass_rowwise<T, N, MODE, P, MI, INLINE_EXACT>(img, perm, slot_rank, lane);
+    if constexpr (RowwiseOk<N, MODE>::value) {
+        prepass_rowwise<T, N, MODE, P, MI, INLINE_EXACT, VEC>(img, perm, slot_rank, lane);
     } else {
     int prow[MI];  // original row sitting at position `lane`
     unsigned multi[MI];
@@ -279,14 +294,14 @@ __device__ __forceinline__ void prepass_warp_ptrs(const T* const (&img)[MI], int
 }
 
 // MI matrices of one tile: img0 + m * MS, perm0 + m * N
-template <typename T, int N, int MODE, int P, int MS, int MI, bool INLINE_EXACT = false>
+template <typename T, int N, int MODE, int P, int MS, int MI, bool INLINE_EXACT = false, bool VEC = false>
 __device__ __forceinline__ void prepass_warp(const T* __restrict__ img0, int* __restrict__ perm0,
                                              const int8_t* __restrict__ slot_rank, int lane) {
     const T* img[MI];
     int* perm[MI];
 #pragma unroll
     for (int m = 0; m < MI; ++m) { img[m] = img0 + m * MS; perm[m] = perm0 + m * N; }
-    prepass_warp_ptrs<T, N, MODE, P, MI, INLINE_EXACT>(img, perm, slot_rank, lane);
+    prepass_warp_ptrs<T, N, MODE, P, MI, INLINE_EXACT, VEC>(img, perm, slot_rank, lane);
 }
 
 // generic sub-warp pre-pass on a strided image (N <= 16): see pivot_prepass in lub_kernel.cuh

@@ -47,13 +47,24 @@ constexpr ScStrides pick_sc_strides(int n, int gr, int gc, int cm, int ew) {
     return s;
 }
 
+#ifndef LUB_V3_VECPIV
+#define LUB_V3_VECPIV 1
+#endif
+
 template <typename T, int N, int GR, int GC, int MODE>
 struct V3Layout {
     static constexpr int ES = sizeof(T);
     static constexpr int EW = ES / 4;
     static constexpr int EPV = 16 / ES;
-    static constexpr bool SC = (MODE != kModeNone);  // element-granular image, odd row stride
     static constexpr int CHV = (N % EPV == 0) ? EPV : ((EPV == 4 && N % 2 == 0) ? 2 : 1);
+    // The row-wise pivot search reads whole rows at static addresses, so it can use the 16-byte
+    // image of the no-pivot path (vector staging: 4x fewer LDS/STS instructions); the position-wise
+    // search walks columns through a dynamic row and needs the element-granular odd-stride image.
+    // (only when the 16-byte chunks split evenly over the lane columns: otherwise the chunk
+    // granularity pads LC and the extra FMA work costs more than the staging saves -- N=24: +12 %)
+    static constexpr bool VECPIV = (LUB_V3_VECPIV != 0) && MODE != kModeNone && N > 16 && CHV == EPV &&
+                                   ((N / EPV) % GC) == 0 && rowwise_prepass_ok(N, MODE);
+    static constexpr bool SC = (MODE != kModeNone) && !VECPIV;  // element-granular image, odd row stride
     static constexpr int CH = SC ? 1 : CHV;
     static constexpr int G = GR * GC;
     static_assert(G >= 1 && G <= 32 && (32 % G) == 0, "G must divide 32");
@@ -74,7 +85,7 @@ struct V3Layout {
     static constexpr int MS = N * P + MPAD;
     static constexpr bool ALIGNED = ((MPW * N * N * ES) % 16) == 0;  // every tile span starts on 16 bytes
     static constexpr int IMG_BYTES = roundup_(MPW * MS * ES, 16) + 16;
-    static constexpr int PERM_BYTES = SC ? roundup_(MPW * N * 4, 16) : 0;
+    static constexpr int PERM_BYTES = (MODE != kModeNone) ? roundup_(MPW * N * 4, 16) : 0;
     static constexpr int WARP_BYTES = IMG_BYTES + PERM_BYTES;
     static constexpr int HEADER_BYTES = 64;
     static constexpr int CPR16 = N * ES / 16;
@@ -221,7 +232,7 @@ lub_v3_kernel(T* __restrict__ A, int32_t* __restrict__ piv, long long batch) {
                 constexpr int MI = (MPW < 4) ? MPW : 4;
 #pragma unroll 1
                 for (int m = 0; m < MPW; m += MI)
-                    prepass_warp<T, N, MODE, P, MS, MI>(img + m * MS, perm_all + m * N, slot_rank, lane);
+                    prepass_warp<T, N, MODE, P, MS, MI, false, L::VECPIV>(img + m * MS, perm_all + m * N, slot_rank, lane);
             } else {
                 prepass_group<T, N, G, MODE, P>(mimg, perm, slot_rank, g);
             }
