@@ -122,6 +122,26 @@ __device__ __forceinline__ void copy_in_padded(unsigned char* __restrict__ img, 
     for (; q < nchunks; q += 32) d[dst_of(q)] = ld_stream16(s + q);
 }
 
+// same mapping, asynchronous (LDGSTS): no registers, the warp does not wait
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int K> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(K) : "memory"); }
+
+template <typename T, typename L, int N>
+__device__ __forceinline__ void copy_in_padded_async(unsigned char* __restrict__ img, const T* __restrict__ src,
+                                                     int nchunks, int lane) {
+    const uint4* s = reinterpret_cast<const uint4*>(src);
+    uint4* d = reinterpret_cast<uint4*>(img);
+    for (int q = lane; q < nchunks; q += 32) {
+        const int rowidx = q / L::CPR16;
+        int o = q + rowidx * L::RPAD16;
+        if (L::MPAD16 != 0) o += (rowidx / N) * L::MPAD16;
+        cp_async16(d + o, s + q);
+    }
+}
+
 template <typename T, typename L, int N>
 __device__ __forceinline__ void copy_out_padded(T* __restrict__ dst, const unsigned char* __restrict__ img,
                                                 int nchunks, int lane) {

@@ -1,0 +1,334 @@
+// lub_tma.cuh -- TMA-staged variant of the in-register Gauss-Jordan kernel (lub_v3.cuh) for the
+// sizes whose rows are exactly one 128-byte line (N = 32 fp32 -- the headline configuration of
+// parallel_pivot/luBatchedInplace.cu -- and N = 16 fp64).
+//
+// Why: lub_v3_kernel is bound by the LSU pipe (shared-memory wavefronts + shuffles + LDG/STG,
+// profiles/r01_prof_headline_*.md: ~616 wavefronts per matrix, 66 % of the pipe's peak).  About a
+// quarter of those wavefronts only move the tile between HBM and shared memory.  Here that part
+// is done by the TMA unit instead: one lane issues cp.async.bulk.tensor (3-D box: N x N x MPW
+// matrices) into a 128-byte-swizzled image and, for the pivoting modes, one bulk tensor store
+// writes the finished tile back.  The swizzle (16-byte chunk index ^ row % 8) makes both the
+// row-wise pivot search (lane = row, LDS.128 along the row) and the permuted register load free
+// of systematic bank conflicts without any padding, which is what TMA needs (a dense box).
+// Without pivoting the results leave straight from the registers: every lane owns whole
+// 32-byte sectors of its rows.
+#pragma once
+#include <cuda.h>
+#include "lub_v3.cuh"
+
+namespace lub {
+
+// ---- PTX wrappers ----------------------------------------------------------------------------
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(void* bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(void* bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(void* bar, unsigned parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "LUB_WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra LUB_DONE_%=;\n"
+        "bra LUB_WAIT_%=;\n"
+        "LUB_DONE_%=:\n"
+        "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, void* bar, int c0, int c1, int c2) {
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+                 ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, const void* src, int c0, int c1, int c2) {
+    asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
+                 ::"l"(map), "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// ---- layout -----------------------------------------------------------------------------------
+template <typename T, int N, int GR, int GC, int MODE>
+struct TmaLayout {
+    static constexpr int ES = sizeof(T);
+    static constexpr int EPV = 16 / ES;
+    static constexpr int RB = N * ES;  // row bytes
+    static_assert(RB == 128, "one row = one 128-byte swizzle line");
+    static constexpr int G = GR * GC;
+    static_assert(G >= 1 && G <= 32 && (32 % G) == 0, "G must divide 32");
+    static constexpr int MPW = 32 / G;
+    static constexpr int CH = EPV;
+    static constexpr int CPR = N / CH;  // 16-byte chunks per row (8)
+    static_assert(CPR % GC == 0, "chunks must split evenly over the lane columns");
+    static constexpr int CPL = CPR / GC;
+    static constexpr int LC = CPL * CH;
+    static constexpr int LR = (N + GR - 1) / GR;
+    static constexpr int MAT_BYTES = N * RB;
+    static constexpr int IMG_BYTES = MPW * MAT_BYTES;
+    static_assert(IMG_BYTES % 1024 == 0, "swizzle atoms are 1 KB");
+    static constexpr int PERM_BYTES = (MODE != kModeNone) ? MPW * N * 4 : 0;
+    static constexpr int HEADER_BYTES = 64;  // slot ranks of the reference tree (exact tie-break path)
+    static constexpr int smem_bytes(int warps) {  // + 1 KB slack to align the images by hand
+        return 1024 + warps * (IMG_BYTES + PERM_BYTES) + warps * 8 + HEADER_BYTES;
+    }
+};
+
+// byte offset of element (row, col) inside one matrix of the swizzled image
+template <int RB, int ES>
+__device__ __forceinline__ int swz_off(int row, int col) { return row * RB + ((col * ES) ^ ((row & 7) << 4)); }
+
+// Exact warp-wide pivot search on the swizzled image (explicit tree priorities): the rare path for
+// matrices with equal |values| in one column.  Same search as prepass_group (lub_fast.cuh).
+template <typename T, int N, int MODE>
+__device__ __noinline__ void prepass_exact_swz(const unsigned char* mimg, int* perm, const int8_t* slot_rank, int lane) {
+    using U = typename FpBits<T>::U;
+    constexpr int RB = N * (int)sizeof(T), ES = sizeof(T);
+    for (int i = lane; i < N; i += 32) perm[i] = i;
+    __syncwarp();
+    for (int k = 0; k < N - 1; ++k) {
+        U best_v = FpBits<T>::absbits(*reinterpret_cast<const T*>(mimg + swz_off<RB, ES>(perm[k], k)));
+        unsigned best_p = 0;
+        for (int t = lane; t < N - 1 - k; t += 32) {
+            int pr;
+            if (MODE == kModeParallel) {
+                pr = slot_rank[t];
+                if (pr < 0) continue;
+            } else {
+                pr = t;
+            }
+            const U v = FpBits<T>::absbits(*reinterpret_cast<const T*>(mimg + swz_off<RB, ES>(perm[k + 1 + t], k)));
+            const unsigned p = ((unsigned)(pr + 1) << 8) | (unsigned)(t + 1);
+            if (v > best_v || (v == best_v && p < best_p)) { best_v = v; best_p = p; }
+        }
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+            const U ov = __shfl_xor_sync(0xffffffffu, best_v, off);
+            const unsigned op = __shfl_xor_sync(0xffffffffu, best_p, off);
+            if (ov > best_v || (ov == best_v && op < best_p)) { best_v = ov; best_p = op; }
+        }
+        __syncwarp();
+        if (lane == 0 && best_p != 0) {
+            const int p = k + (int)(best_p & 0xffu);
+            const int tmp = perm[k];
+            perm[k] = perm[p];
+            perm[p] = tmp;
+        }
+        __syncwarp();
+    }
+}
+
+// Row-wise pivot search (see prepass_rowwise in lub_fast.cuh) on the swizzled image: lane = original
+// row, one LDS.128 per 16-byte chunk of the row, conflict-free because of the swizzle.
+template <typename T, int N, int MODE, int MI>
+__device__ __forceinline__ void prepass_rowwise_swz(const unsigned char* img0, int* perm0, const int8_t* slot_rank, int lane) {
+    using U = typename FpBits<T>::U;
+    constexpr int ES = sizeof(T), EPV = 16 / ES, RB = N * ES, MAT = N * RB;
+    const int row = (lane < N) ? lane : 0;
+    const unsigned char* rowp = img0 + row * RB;
+    const int xr = (row & 7) << 4;
+    U alive[MI];
+    int when[MI];
+#pragma unroll
+    for (int m = 0; m < MI; ++m) { alive[m] = (lane < N) ? ~U(0) : U(0); when[m] = N - 1; }
+    T x[MI][EPV];
+#pragma unroll
+    for (int k = 0; k < N - 1; ++k) {
+        if ((k % EPV) == 0) {
+#pragma unroll
+            for (int m = 0; m < MI; ++m)
+                ld_vec<T, EPV>(reinterpret_cast<const T*>(rowp + m * MAT + (((k / EPV) << 4) ^ xr)), x[m]);
+        }
+        U key[MI], mx[MI];
+#pragma unroll
+        for (int m = 0; m < MI; ++m) key[m] = ((FpBits<T>::absbits(x[m][k % EPV]) << 1) | U(1)) & alive[m];
+#pragma unroll
+        for (int m = 0; m < MI; ++m) mx[m] = warp_max_bits(key[m]);
+#pragma unroll
+        for (int m = 0; m < MI; ++m) {
+            const bool hit = key[m] == mx[m];
+            when[m] = hit ? k : when[m];
+            alive[m] = hit ? U(0) : alive[m];
+        }
+    }
+#pragma unroll
+    for (int m = 0; m < MI; ++m) {
+        const bool ok = __popc(__ballot_sync(0xffffffffu, alive[m] != U(0))) == 1;  // warp-uniform
+        if (ok) {
+            if (lane < N) perm0[m * N + when[m]] = lane;
+        } else {
+            prepass_exact_swz<T, N, MODE>(img0 + m * MAT, perm0 + m * N, slot_rank, lane);
+        }
+    }
+}
+
+// One warp = one tile of MPW matrices; persistent over tiles.  BSYNC as in lub_v3_kernel.
+template <typename T, int N, int GR, int GC, int MODE, int MINB = 2, bool BSYNC = true>
+__global__ void __launch_bounds__(kMaxThreads, MINB)
+lub_tma_kernel(const __grid_constant__ CUtensorMap tmap, T* __restrict__ A, int32_t* __restrict__ piv, long long batch) {
+    using L = TmaLayout<T, N, GR, GC, MODE>;
+    constexpr int G = L::G, MPW = L::MPW, LR = L::LR, LC = L::LC, CH = L::CH, CPL = L::CPL;
+    constexpr int RB = L::RB, ES = L::ES, MAT = L::MAT_BYTES;
+    extern __shared__ unsigned char smem_dyn[];
+
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    const int nwarps = blockDim.x >> 5;
+    // carve: [images, 1 KB aligned][perm][mbarriers][slot ranks]
+    unsigned char* base = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);
+    unsigned char* img = base + (size_t)warp * L::IMG_BYTES;
+    unsigned char* after = base + (size_t)nwarps * L::IMG_BYTES;
+    int* perm_all = reinterpret_cast<int*>(after + (size_t)warp * L::PERM_BYTES);
+    unsigned long long* bar = reinterpret_cast<unsigned long long*>(after + (size_t)nwarps * L::PERM_BYTES) + warp;
+    int8_t* slot_rank = reinterpret_cast<int8_t*>(after + (size_t)nwarps * L::PERM_BYTES + (size_t)nwarps * 8);
+
+    if (MODE == kModeParallel && threadIdx.x < N) slot_rank[threadIdx.x] = (int8_t)tree_slot_rank(threadIdx.x, N);
+    if (lane == 0) mbar_init(bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    __syncthreads();
+
+    const int g = lane % G;
+    const int ml = lane / G;
+    const int gr = g / GC;
+    const int gc = g % GC;
+    const int grp_base = ml * G;
+    unsigned parity = 0;
+
+    const long long ntiles = (batch + MPW - 1) / MPW;
+#pragma unroll 1
+    for (long long tbase = (long long)blockIdx.x * nwarps; tbase < ntiles; tbase += (long long)gridDim.x * nwarps) {
+        if (BSYNC) __syncthreads();
+        const long long tile = tbase + warp;
+        if (tile >= ntiles) continue;
+        const long long first = tile * MPW;
+        const int nm = (batch - first < MPW) ? (int)(batch - first) : MPW;
+        T* gspan = A + first * (long long)(N * N);
+
+        // ---- HBM -> swizzled image, by the TMA unit (matrices past the batch end read as zero) ----
+        if (lane == 0) {
+            if (MODE != kModeNone) tma_store_wait_read();  // last round's tile has left the image
+            mbar_expect_tx(bar, (unsigned)L::IMG_BYTES);
+            tma_load_3d(img, &tmap, bar, 0, 0, (int)first);
+        }
+        mbar_wait(bar, parity);
+        parity ^= 1u;
+
+        unsigned char* mimg = img + ml * MAT;
+        int* perm = perm_all + ml * N;
+        if (MODE != kModeNone) {
+            constexpr int MI = (MPW < 2) ? MPW : 2;
+#pragma unroll 1
+            for (int m = 0; m < MPW; m += MI)
+                prepass_rowwise_swz<T, N, MODE, MI>(img + m * MAT, perm_all + m * N, slot_rank, lane);
+            __syncwarp();
+        }
+
+        // ---- registers <- image: rows permuted, LR x LC block per lane ---------------------
+        T a[LR][LC];
+#pragma unroll
+        for (int li = 0; li < LR; ++li) {
+            const int i = li * GR + gr;
+            const bool rok = (li * GR + GR - 1 < N) || (i < N);
+            int prow = rok ? i : 0;
+            if (MODE != kModeNone) prow = rok ? perm[i] : 0;
+            const unsigned char* rowp = mimg + prow * RB;
+            const int xr = (prow & 7) << 4;
+#pragma unroll
+            for (int q = 0; q < CPL; ++q) {
+                if (rok) {
+                    ld_vec<T, CH>(reinterpret_cast<const T*>(rowp + (((gc * CPL + q) << 4) ^ xr)), &a[li][q * CH]);
+                } else {
+#pragma unroll
+                    for (int w = 0; w < CH; ++w) a[li][q * CH + w] = T(0);
+                }
+            }
+        }
+
+        T dinv[LR];
+#pragma unroll
+        for (int li = 0; li < LR; ++li) dinv[li] = T(0);
+        gj_eliminate<T, N, GR, GC, CH, CPL, LR, LC>(a, dinv, gr, gc, grp_base);
+
+        // ---- scale by 1/pivot; undo the row permutation as a column scatter -------------------
+#pragma unroll
+        for (int li = 0; li < LR; ++li) {
+#pragma unroll
+            for (int lj = 0; lj < LC; ++lj) a[li][lj] *= dinv[li];
+        }
+        if (MODE == kModeNone) {
+            T* gm = gspan + (size_t)ml * (N * N) + gc * LC;
+#pragma unroll
+            for (int li = 0; li < LR; ++li) {
+                const int i = li * GR + gr;
+                const bool rok = (ml < nm) && ((li * GR + GR - 1 < N) || (i < N));
+#pragma unroll
+                for (int q = 0; q < CPL; ++q)
+                    if (rok) st_vec<T, CH>(gm + i * N + q * CH, &a[li][q * CH]);
+            }
+        } else {
+            int pcb[LC];  // byte offset of the destination column inside a row
+#pragma unroll
+            for (int lj = 0; lj < LC; ++lj) pcb[lj] = perm[gc * LC + lj] * ES;
+            __syncwarp();  // all lanes hold their blocks and columns: the image may be overwritten
+#pragma unroll
+            for (int li = 0; li < LR; ++li) {
+                const int i = li * GR + gr;
+                const bool rok = (li * GR + GR - 1 < N) || (i < N);
+                unsigned char* rowp = mimg + i * RB;
+                const int xr = (i & 7) << 4;
+#pragma unroll
+                for (int lj = 0; lj < LC; ++lj)
+                    if (rok) *reinterpret_cast<T*>(rowp + (pcb[lj] ^ xr)) = a[li][lj];
+            }
+            fence_proxy_async();  // generic-proxy writes -> visible to the TMA unit
+            __syncwarp();
+            if (lane == 0) {
+                tma_store_3d(&tmap, img, 0, 0, (int)first);  // rows past the batch end are clipped
+                tma_store_commit();
+            }
+        }
+        int32_t* pivp = piv;
+        asm volatile("" : "+l"(pivp));  // opaque: no second copy of the tile loop for piv == NULL
+        if (pivp != nullptr) {
+            int32_t* pdst = pivp + first * N;
+            for (int e = lane; e < nm * N; e += 32)
+                pdst[e] = (MODE != kModeNone) ? perm_all[e] : (e % N);
+        }
+        __syncwarp();
+    }
+    if (MODE != kModeNone && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // stores complete
+}
+
+// ---- host: tensor map over the batch viewed as [batch][N][N], box = one warp tile ----------------
+using EncodeTiledFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+inline EncodeTiledFn encode_tiled_fn() {
+    static EncodeTiledFn fn = []() -> EncodeTiledFn {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) != cudaSuccess) return nullptr;
+        if (qres != cudaDriverEntryPointSuccess) return nullptr;
+        return reinterpret_cast<EncodeTiledFn>(p);
+    }();
+    return fn;
+}
+
+template <typename T>
+inline cudaError_t make_batch_tmap(CUtensorMap* map, void* A, int n, long long batch, int mpw) {
+    EncodeTiledFn enc = encode_tiled_fn();
+    if (!enc) return cudaErrorNotSupported;
+    const cuuint64_t dims[3] = {(cuuint64_t)n, (cuuint64_t)n, (cuuint64_t)batch};
+    const cuuint64_t strides[2] = {(cuuint64_t)n * sizeof(T), (cuuint64_t)n * n * sizeof(T)};
+    const cuuint32_t box[3] = {(cuuint32_t)n, (cuuint32_t)n, (cuuint32_t)mpw};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    const CUtensorMapDataType dt = (sizeof(T) == 4) ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT64;
+    const CUresult r = enc(map, dt, 3, A, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                           CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? cudaSuccess : cudaErrorInvalidValue;
+}
+
+}  // namespace lub

@@ -87,6 +87,9 @@ struct V3Layout {
     static constexpr int IMG_BYTES = roundup_(MPW * MS * ES, 16) + 16;
     static constexpr int PERM_BYTES = (MODE != kModeNone) ? roundup_(MPW * N * 4, 16) : 0;
     static constexpr int WARP_BYTES = IMG_BYTES + PERM_BYTES;
+    // prefetching kernel: + a one-matrix output buffer (pivot modes only)
+    static constexpr int OUT_BYTES = (MODE != kModeNone) ? roundup_(MS * ES, 16) : 0;
+    static constexpr int WARP_BYTES_PF = IMG_BYTES + OUT_BYTES + PERM_BYTES;
     static constexpr int HEADER_BYTES = 64;
     static constexpr int CPR16 = N * ES / 16;
     static constexpr int RPAD16 = (P - N) * ES / 16, MPAD16 = MPAD * ES / 16;
@@ -169,10 +172,52 @@ __device__ __forceinline__ void copy_out_gather(T* __restrict__ dst, const T* __
 // BSYNC: one block barrier per tile (see the loop).  DBG (tuning harness only): 1 = skip the
 // elimination, 2 = skip the pivot pre-pass (identity permutation), 4 = skip global loads/stores
 // after the first tile.  DBG is 0 in the product.
-template <typename T, int N, int GR, int GC, int MODE, int MINB = 1, bool BSYNC = true, int DBG = 0>
+// In-register Gauss-Jordan on the LR x LC block of every lane: row k and column k travel by
+// shuffles, rows are scaled by 1/pivot only at the end (dinv), column k is overwritten with the
+// multipliers as it is cleared (in-place inverse).  Shared by lub_v3_kernel and lub_tma_kernel.
+template <typename T, int N, int GR, int GC, int CH, int CPL, int LR, int LC>
+__device__ __forceinline__ void gj_eliminate(T (&a)[LR][LC], T (&dinv)[LR], int gr, int gc, int grp_base) {
+    constexpr int G = GR * GC;
+#pragma unroll
+    for (int k = 0; k < N; ++k) {
+        const int gro = k % GR, lk = k / GR;
+        const int cj = k / CH, gco = cj / CPL, ck = (cj % CPL) * CH + (k % CH);
+        const bool own_row = (GR == 1) || (gr == gro);
+        const bool own_col = (GC == 1) || (gc == gco);
+        T r[LC], c[LR];
+#pragma unroll
+        for (int lj = 0; lj < LC; ++lj)
+            r[lj] = (GR > 1) ? shfl_t(a[lk][lj], grp_base + gro * GC + gc) : a[lk][lj];
+#pragma unroll
+        for (int li = 0; li < LR; ++li)
+            c[li] = (GC > 1) ? shfl_t(a[li][ck], grp_base + gr * GC + gco) : a[li][ck];
+        // straight from the owner (not via r[ck]): all shuffles of a step leave in one batch
+        const T pv = (G > 1) ? shfl_t(a[lk][ck], grp_base + gro * GC + gco) : a[lk][ck];
+        const T rinv = rcp_t(pv);
+        set_if(own_col, r[ck], T(1));
+        T nf[LR];
+#pragma unroll
+        for (int li = 0; li < LR; ++li) nf[li] = -(c[li] * rinv);
+        set_if(own_row, nf[lk], T(0));
+        const T diag = sel_t(own_row, T(1), T(0));
+#pragma unroll
+        for (int li = 0; li < LR; ++li) set_if(own_col, a[li][ck], (li == lk) ? diag : T(0));
+#pragma unroll
+        for (int li = 0; li < LR; ++li) row_update<LC>(a[li], r, nf[li]);
+        set_if(own_row, dinv[lk], rinv);
+    }
+}
+
+// PF (16-byte image layouts): the tile image is free again as soon as the registers are loaded, so
+// the NEXT tile is fetched into it with cp.async while this one is eliminated -- no warp waits on
+// HBM for its input.  The results then leave through a separate one-matrix output buffer, one
+// matrix of the tile at a time (pivot modes: the column scatter needs shared memory), or straight
+// from the registers (no pivoting: every lane owns whole 32-byte sectors of its rows).
+template <typename T, int N, int GR, int GC, int MODE, int MINB = 1, bool BSYNC = true, int DBG = 0, bool PF = false>
 __global__ void __launch_bounds__(kMaxThreads, MINB)
 lub_v3_kernel(T* __restrict__ A, int32_t* __restrict__ piv, long long batch) {
     using L = V3Layout<T, N, GR, GC, MODE>;
+    static_assert(!PF || L::ROWVEC, "prefetch needs the 16-byte image");
     constexpr int G = L::G, MPW = L::MPW, LR = L::LR, LC = L::LC, CH = L::CH, CPL = L::CPL, CPR = L::CPR;
     constexpr int P = L::P, MS = L::MS;
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -181,8 +226,9 @@ lub_v3_kernel(T* __restrict__ A, int32_t* __restrict__ piv, long long batch) {
     const int warp = threadIdx.x >> 5;
     const int nwarps = blockDim.x >> 5;
     int8_t* slot_rank = reinterpret_cast<int8_t*>(smem_raw);
-    unsigned char* wbase = smem_raw + L::HEADER_BYTES + (size_t)warp * L::WARP_BYTES;
-    int* perm_all = reinterpret_cast<int*>(wbase + L::IMG_BYTES);
+    unsigned char* wbase = smem_raw + L::HEADER_BYTES + (size_t)warp * (PF ? L::WARP_BYTES_PF : L::WARP_BYTES);
+    unsigned char* obase = wbase + L::IMG_BYTES;  // PF: one-matrix output buffer
+    int* perm_all = reinterpret_cast<int*>(wbase + L::IMG_BYTES + (PF ? L::OUT_BYTES : 0));
 
     if (MODE == kModeParallel) {
         if (threadIdx.x < N) slot_rank[threadIdx.x] = (int8_t)tree_slot_rank(threadIdx.x, N);
@@ -196,6 +242,16 @@ lub_v3_kernel(T* __restrict__ A, int32_t* __restrict__ piv, long long batch) {
     const int grp_base = ml * G;
 
     const long long ntiles = (batch + MPW - 1) / MPW;
+    const long long tstride = (long long)gridDim.x * nwarps;
+    if constexpr (PF) {
+        const long long t0 = (long long)blockIdx.x * nwarps + warp;
+        if (t0 < ntiles) {
+            const long long first0 = t0 * MPW;
+            const int nm0 = (batch - first0 < MPW) ? (int)(batch - first0) : MPW;
+            copy_in_padded_async<T, L, N>(wbase, A + first0 * (long long)(N * N), nm0 * N * L::CPR16, lane);
+        }
+        cp_async_commit();
+    }
 #pragma unroll 1
     for (long long tbase = (long long)blockIdx.x * nwarps; tbase < ntiles; tbase += (long long)gridDim.x * nwarps) {
         // Re-align the block's warps once per tile: they all run the same ~50 KB of straight-line
@@ -207,7 +263,10 @@ lub_v3_kernel(T* __restrict__ A, int32_t* __restrict__ piv, long long batch) {
         const int nm = (batch - first < MPW) ? (int)(batch - first) : MPW;
         T* gspan = A + first * (long long)(N * N);
         T* img;
-        if ((DBG & 4) && tile >= (long long)gridDim.x * nwarps) {
+        if constexpr (PF) {
+            img = reinterpret_cast<T*>(wbase);
+            cp_async_wait<0>();  // this tile, requested one round ago
+        } else if ((DBG & 4) && tile >= (long long)gridDim.x * nwarps) {
             img = reinterpret_cast<T*>(wbase);
         } else if constexpr (L::SC) {
             img = reinterpret_cast<T*>(wbase);
@@ -261,38 +320,22 @@ lub_v3_kernel(T* __restrict__ A, int32_t* __restrict__ piv, long long batch) {
             }
         }
 
+        if constexpr (PF) {
+            __syncwarp();  // every lane has its block: the image can take the next tile
+            const long long nxt = tile + tstride;
+            if (nxt < ntiles) {
+                const long long firstn = nxt * MPW;
+                const int nmn = (batch - firstn < MPW) ? (int)(batch - firstn) : MPW;
+                copy_in_padded_async<T, L, N>(wbase, A + firstn * (long long)(N * N), nmn * N * L::CPR16, lane);
+            }
+            cp_async_commit();
+        }
+
         // ---- Gauss-Jordan with deferred row scaling; exchange by shuffles ---------------------
         T dinv[LR];
 #pragma unroll
         for (int li = 0; li < LR; ++li) dinv[li] = T(0);
-#pragma unroll
-        for (int k = 0; k < ((DBG & 1) ? 0 : N); ++k) {
-            const int gro = k % GR, lk = k / GR;
-            const int cj = k / CH, gco = cj / CPL, ck = (cj % CPL) * CH + (k % CH);
-            const bool own_row = (GR == 1) || (gr == gro);
-            const bool own_col = (GC == 1) || (gc == gco);
-            T r[LC], c[LR];
-#pragma unroll
-            for (int lj = 0; lj < LC; ++lj)
-                r[lj] = (GR > 1) ? shfl_t(a[lk][lj], grp_base + gro * GC + gc) : a[lk][lj];
-#pragma unroll
-            for (int li = 0; li < LR; ++li)
-                c[li] = (GC > 1) ? shfl_t(a[li][ck], grp_base + gr * GC + gco) : a[li][ck];
-            // straight from the owner (not via r[ck]): all shuffles of a step leave in one batch
-            const T pv = (G > 1) ? shfl_t(a[lk][ck], grp_base + gro * GC + gco) : a[lk][ck];
-            const T rinv = rcp_t(pv);
-            set_if(own_col, r[ck], T(1));
-            T nf[LR];
-#pragma unroll
-            for (int li = 0; li < LR; ++li) nf[li] = -(c[li] * rinv);
-            set_if(own_row, nf[lk], T(0));
-            const T diag = sel_t(own_row, T(1), T(0));
-#pragma unroll
-            for (int li = 0; li < LR; ++li) set_if(own_col, a[li][ck], (li == lk) ? diag : T(0));
-#pragma unroll
-            for (int li = 0; li < LR; ++li) row_update<LC>(a[li], r, nf[li]);
-            set_if(own_row, dinv[lk], rinv);
-        }
+        if (!(DBG & 1)) gj_eliminate<T, N, GR, GC, CH, CPL, LR, LC>(a, dinv, gr, gc, grp_base);
 
         // ---- scale by 1/pivot, undo the row permutation as a column scatter -------------------
         __syncwarp();
@@ -301,7 +344,43 @@ lub_v3_kernel(T* __restrict__ A, int32_t* __restrict__ piv, long long batch) {
 #pragma unroll
             for (int lj = 0; lj < LC; ++lj) a[li][lj] *= ((DBG & 1) ? T(1) : dinv[li]);
         }
-        if (MODE == kModeNone) {
+        if (PF && MODE == kModeNone) {
+            T* gm = gspan + (size_t)ml * (N * N);
+#pragma unroll
+            for (int li = 0; li < LR; ++li) {
+                const int i = li * GR + gr;
+                const bool rok = (ml < nm) && ((li * GR + GR - 1 < N) || (i < N));
+#pragma unroll
+                for (int q = 0; q < CPL; ++q) {
+                    const int cq = gc * CPL + q;
+                    if (rok && ((GC * CPL <= CPR) || (cq < CPR))) st_vec<T, CH>(gm + i * N + cq * CH, &a[li][q * CH]);
+                }
+            }
+        } else if (PF) {
+            int pcol[LC];
+#pragma unroll
+            for (int lj = 0; lj < LC; ++lj) {
+                const int j = gc * LC + lj;
+                pcol[lj] = ((GC * LC <= N) || (j < N)) ? perm[j] : -1;
+            }
+            T* oimg = reinterpret_cast<T*>(obase);
+#pragma unroll 1
+            for (int m = 0; m < nm; ++m) {
+                if (ml == m) {
+#pragma unroll
+                    for (int li = 0; li < LR; ++li) {
+                        const int i = li * GR + gr;
+                        const bool rok = (li * GR + GR - 1 < N) || (i < N);
+#pragma unroll
+                        for (int lj = 0; lj < LC; ++lj)
+                            if (rok && pcol[lj] >= 0) oimg[i * P + pcol[lj]] = a[li][lj];
+                    }
+                }
+                __syncwarp();
+                copy_out_padded<T, L, N>(gspan + (size_t)m * (N * N), obase, N * L::CPR16, lane);
+                __syncwarp();
+            }
+        } else if (MODE == kModeNone) {
 #pragma unroll
             for (int li = 0; li < LR; ++li) {
                 const int i = li * GR + gr;
@@ -329,7 +408,8 @@ lub_v3_kernel(T* __restrict__ A, int32_t* __restrict__ piv, long long batch) {
             }
         }
         __syncwarp();
-        if ((DBG & 4) && tile >= (long long)gridDim.x * nwarps) {
+        if constexpr (PF) {
+        } else if ((DBG & 4) && tile >= (long long)gridDim.x * nwarps) {
         } else if constexpr (L::SC) copy_out_gather<T, L, N>(gspan, img, nm * N * N, lane);
         else if constexpr (L::ROWVEC) copy_out_padded<T, L, N>(gspan, wbase, nm * N * L::CPR16, lane);
         else copy_out<T>(gspan, img, nm * N * N, lane);

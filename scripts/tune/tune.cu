@@ -3,6 +3,7 @@
 // time them side by side on the GPU box.  Build: make -C scripts/tune
 #include <cstdio>
 #include "../../matrixinversion_b200/csrc/lub_v5.cuh"
+#include "../../matrixinversion_b200/csrc/lub_tma.cuh"
 
 using namespace lub;
 
@@ -12,23 +13,24 @@ struct Variant {
     void (*set_attr)(int smem);
     void (*launch)(void*, int*, long long, unsigned, int, int, cudaStream_t);
     int (*occ)(int threads, int smem);
+    int (*smem_of)(int warps) = nullptr;
 };
 
 template <typename T, int N, int GR, int GC, int MODE, int MINB, int DBG = 0>
 struct V3 {
     using L = V3Layout<T, N, GR, GC, MODE>;
     static void set_attr(int smem) {
-        cudaFuncSetAttribute(lub_v3_kernel<T, N, GR, GC, MODE, MINB, (DBG & 8) != 0, (DBG & 7)>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        cudaFuncSetAttribute(lub_v3_kernel<T, N, GR, GC, MODE, MINB, (DBG & 8) != 0, (DBG & 7), (DBG & 16) != 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     }
     static void launch(void* A, int* piv, long long batch, unsigned blocks, int threads, int smem, cudaStream_t s) {
-        lub_v3_kernel<T, N, GR, GC, MODE, MINB, (DBG & 8) != 0, (DBG & 7)><<<blocks, threads, smem, s>>>((T*)A, piv, batch);
+        lub_v3_kernel<T, N, GR, GC, MODE, MINB, (DBG & 8) != 0, (DBG & 7), (DBG & 16) != 0><<<blocks, threads, smem, s>>>((T*)A, piv, batch);
     }
     static int occ(int threads, int smem) {
         int o = 0;
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, lub_v3_kernel<T, N, GR, GC, MODE, MINB, (DBG & 8) != 0, (DBG & 7)>, threads, smem);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, lub_v3_kernel<T, N, GR, GC, MODE, MINB, (DBG & 8) != 0, (DBG & 7), (DBG & 16) != 0>, threads, smem);
         return o;
     }
-    static Variant make(const char* name) { return Variant{name, L::MPW, L::WARP_BYTES, L::HEADER_BYTES, set_attr, launch, occ}; }
+    static Variant make(const char* name) { return Variant{name, L::MPW, (DBG & 16) ? L::WARP_BYTES_PF : L::WARP_BYTES, L::HEADER_BYTES, set_attr, launch, occ}; }
 };
 
 template <typename T, int N, int GR, int GC, int MODE, int MINB, int DBG = 0>
@@ -64,6 +66,28 @@ struct V5 {
     }
     static Variant make(const char* name) { return Variant{name, L::MPW, -(NPW + NCW) * 32, L::SMEM_BYTES, set_attr, launch, occ}; }
 };
+
+// TMA-staged kernel: warp_bytes == -1000000 marks it; launch builds the tensor map per call
+template <typename T, int N, int GR, int GC, int MODE, int MINB, int BS>
+struct VT {
+    using L = TmaLayout<T, N, GR, GC, MODE>;
+    static void set_attr(int smem) {
+        cudaFuncSetAttribute(lub_tma_kernel<T, N, GR, GC, MODE, MINB, BS != 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    }
+    static void launch(void* A, int* piv, long long batch, unsigned blocks, int threads, int smem, cudaStream_t s) {
+        CUtensorMap map;
+        if (make_batch_tmap<T>(&map, A, N, batch, L::MPW) != cudaSuccess) { printf("tensor map failed\n"); return; }
+        lub_tma_kernel<T, N, GR, GC, MODE, MINB, BS != 0><<<blocks, threads, smem, s>>>(map, (T*)A, piv, batch);
+    }
+    static int occ(int threads, int smem) {
+        int o = 0;
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, lub_tma_kernel<T, N, GR, GC, MODE, MINB, BS != 0>, threads, smem);
+        return o;
+    }
+    static Variant make(const char* name) { return Variant{name, L::MPW, -1000000, 0, set_attr, launch, occ, &L::smem_bytes}; }
+};
+#define VART(T, N, GR, GC, MODE, MINB, BS) VT<T, N, GR, GC, MODE, MINB, BS>::make(#T " N=" #N " " #GR "x" #GC " mode" #MODE " minb" #MINB " bs" #BS " tma")
+
 #define VAR5(T, N, GR, GC, MODE, NPW, NCW, NB, PRE) V5<T, N, GR, GC, MODE, NPW, NCW, NB, PRE>::make(#T " N=" #N " " #GR "x" #GC " mode" #MODE " p" #NPW " c" #NCW " nb" #NB " opt" #PRE " v5")
 
 #define VAR(T, N, GR, GC, MODE, MINB) V<T, N, GR, GC, MODE, MINB>::make(#T " N=" #N " " #GR "x" #GC " mode" #MODE " minb" #MINB)
@@ -78,6 +102,20 @@ extern "C" int tune_count() { return (int)(sizeof(variants) / sizeof(variants[0]
 extern "C" const char* tune_name(int i) { return variants[i].name; }
 extern "C" int tune_launch(int i, void* A, int* piv, long long batch, int threads, void* stream, int* occ_out, int* blocks_out) {
     Variant& v = variants[i];
+    if (v.smem_of) {
+        const int warps = threads / 32;
+        const int smem = v.smem_of(warps);
+        v.set_attr(smem);
+        const int occ = v.occ(threads, smem);
+        if (occ < 1) return -1;
+        const long long ntiles = (batch + v.mpw - 1) / v.mpw;
+        long long blocks = (ntiles + warps - 1) / warps;
+        if (blocks > 148ll * occ) blocks = 148ll * occ;
+        if (occ_out) *occ_out = occ;
+        if (blocks_out) *blocks_out = (int)blocks;
+        v.launch(A, piv, batch, (unsigned)blocks, threads, smem, (cudaStream_t)stream);
+        return cudaGetLastError() == cudaSuccess ? 0 : -2;
+    }
     if (v.warp_bytes < 0) {  // persistent producer/consumer kernel: one block per SM
         threads = -v.warp_bytes;
         const int smem = v.header;
