@@ -9,6 +9,7 @@
 #include "lub_fast.cuh"
 #include "lub_v3.cuh"
 #include "lub_v4.cuh"
+#include "lub_tma.cuh"
 
 namespace lub {
 
@@ -94,6 +95,14 @@ struct V3Cfg {
     static constexpr int MINB = 2;  // 128 registers per thread, two 256-thread blocks per SM
 };
 
+#ifndef LUB_USE_TMA
+#define LUB_USE_TMA 1
+#endif
+constexpr bool kUseTma = LUB_USE_TMA != 0;
+// the TMA kernel wants the 16-byte chunks of a row to split evenly over the lane columns
+template <typename T, int N, int GR, int GC>
+struct TmaOk { static constexpr bool value = ((N * (int)sizeof(T) / 16) % GC) == 0 && (32 % (GR * GC)) == 0; };
+
 constexpr int kMaxDevices = 64;
 
 struct KernelCache { int ready_threads; int blocks_per_sm; int sms; int regs; };
@@ -140,10 +149,49 @@ cudaError_t launch(void* A, int32_t* piv, long long batch, int threads, cudaStre
     static KernelCache cache_fast[kMaxDevices] = {}, cache_gen[kMaxDevices] = {};
     int smem, mpw, g;
     KernelCache* c;
+    // rows of exactly 128 bytes (N = 32 fp32, N = 16 fp64): the TMA-staged kernel (lub_tma.cuh)
+    constexpr bool USE_TMA = kUseTma && (N * sizeof(T) == 128) && TmaOk<T, N, VC::GR, VC::GC>::value;
+    if constexpr (USE_TMA) {
+        if (fast) {
+            using TL = TmaLayout<T, N, VC::GR, VC::GC, MODE>;
+            constexpr bool BS = (MODE != kModeNone);  // per-tile block barrier: pays only with the pivot search
+            auto kern = lub_tma_kernel<T, N, VC::GR, VC::GC, MODE, VC::MINB, BS>;
+            smem = TL::smem_bytes(warps); mpw = TL::MPW; g = TL::G; c = &cache_fast[dev];
+            err = prepare(kern, *c, dev, threads, smem);
+            if (err != cudaSuccess) return err;
+            const long long ntiles = (batch + mpw - 1) / mpw;
+            long long blocks = (ntiles + warps - 1) / warps;
+            const long long resident = (long long)c->sms * c->blocks_per_sm;
+            if (blocks > resident) blocks = resident;
+            if (info) {
+                info->threads_per_block = threads; info->threads_per_matrix = g; info->matrices_per_block = warps * mpw;
+                info->num_blocks = blocks; info->dyn_smem_bytes = smem; info->regs_per_thread = c->regs;
+                info->blocks_per_sm = c->blocks_per_sm;
+            }
+            if (dry_run || batch == 0) return cudaSuccess;
+            CUtensorMap map;
+            err = make_batch_tmap<T>(&map, A, N, batch, mpw);
+            if (err != cudaSuccess) return err;
+            kern<<<(unsigned)blocks, threads, smem, stream>>>(map, static_cast<T*>(A), piv, batch);
+            return cudaGetLastError();
+        }
+    }
+    // no pivoting on the 16-byte image: the next tile is prefetched with cp.async while this one is
+    // eliminated and the results leave straight from the registers (12-22 % faster, N = 16..24,
+    // profiles/r01_tune_prefetch.jsonl); no per-tile block barrier there
+    constexpr bool V3_PF = !USE_V4 && (MODE == kModeNone) && V3Layout<T, N, VC::GR, VC::GC, MODE>::ROWVEC;
     if (fast) {
-        smem = FL::HEADER_BYTES + warps * FL::WARP_BYTES; mpw = FL::MPW; g = FL::G; c = &cache_fast[dev];
-        if constexpr (USE_V4) err = prepare(lub_v4_kernel<T, N, VC::GR, VC::GC, MODE, VC::MINB, false, 0>, *c, dev, threads, smem);
-        else err = prepare(lub_v3_kernel<T, N, VC::GR, VC::GC, MODE, VC::MINB>, *c, dev, threads, smem);
+        mpw = FL::MPW; g = FL::G; c = &cache_fast[dev];
+        if constexpr (USE_V4) {
+            smem = FL::HEADER_BYTES + warps * FL::WARP_BYTES;
+            err = prepare(lub_v4_kernel<T, N, VC::GR, VC::GC, MODE, VC::MINB, false, 0>, *c, dev, threads, smem);
+        } else if constexpr (V3_PF) {
+            smem = FL::HEADER_BYTES + warps * FL::WARP_BYTES_PF;
+            err = prepare(lub_v3_kernel<T, N, VC::GR, VC::GC, MODE, VC::MINB, false, 0, true>, *c, dev, threads, smem);
+        } else {
+            smem = FL::HEADER_BYTES + warps * FL::WARP_BYTES;
+            err = prepare(lub_v3_kernel<T, N, VC::GR, VC::GC, MODE, VC::MINB>, *c, dev, threads, smem);
+        }
     } else {
         smem = GL::HEADER_BYTES + warps * GL::WARP_BYTES; mpw = GL::MPW; g = GL::G; c = &cache_gen[dev];
         err = prepare(lub_invert_kernel<T, N, AutoCfg<T, N, MODE>::GR, AutoCfg<T, N, MODE>::GC, MODE>, *c, dev, threads, smem);
@@ -167,6 +215,9 @@ cudaError_t launch(void* A, int32_t* piv, long long batch, int threads, cudaStre
     if (fast) {
         if constexpr (USE_V4)
             lub_v4_kernel<T, N, VC::GR, VC::GC, MODE, VC::MINB, false, 0>
+                <<<(unsigned)blocks, threads, smem, stream>>>(static_cast<T*>(A), piv, batch);
+        else if constexpr (V3_PF)
+            lub_v3_kernel<T, N, VC::GR, VC::GC, MODE, VC::MINB, false, 0, true>
                 <<<(unsigned)blocks, threads, smem, stream>>>(static_cast<T*>(A), piv, batch);
         else
             lub_v3_kernel<T, N, VC::GR, VC::GC, MODE, VC::MINB>

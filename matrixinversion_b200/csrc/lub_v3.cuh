@@ -344,7 +344,7 @@ lub_v3_kernel(T* __restrict__ A, int32_t* __restrict__ piv, long long batch) {
 #pragma unroll
             for (int lj = 0; lj < LC; ++lj) a[li][lj] *= ((DBG & 1) ? T(1) : dinv[li]);
         }
-        if (PF && MODE == kModeNone) {
+        if constexpr (PF && MODE == kModeNone) {
             T* gm = gspan + (size_t)ml * (N * N);
 #pragma unroll
             for (int li = 0; li < LR; ++li) {
@@ -356,7 +356,7 @@ lub_v3_kernel(T* __restrict__ A, int32_t* __restrict__ piv, long long batch) {
                     if (rok && ((GC * CPL <= CPR) || (cq < CPR))) st_vec<T, CH>(gm + i * N + cq * CH, &a[li][q * CH]);
                 }
             }
-        } else if (PF) {
+        } else if constexpr (PF) {
             int pcol[LC];
 #pragma unroll
             for (int lj = 0; lj < LC; ++lj) {
@@ -380,7 +380,7 @@ lub_v3_kernel(T* __restrict__ A, int32_t* __restrict__ piv, long long batch) {
                 copy_out_padded<T, L, N>(gspan + (size_t)m * (N * N), obase, N * L::CPR16, lane);
                 __syncwarp();
             }
-        } else if (MODE == kModeNone) {
+        } else if constexpr (MODE == kModeNone) {
 #pragma unroll
             for (int li = 0; li < LR; ++li) {
                 const int i = li * GR + gr;
