@@ -278,7 +278,7 @@ def main():
         except Exception:
             traffic = None
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": traffic, "peak_source": peak_src, "kernel": "lub_v3_kernel<%s,N=%d,mode=%s>" % (a.dtype, n, a.mode),
+                "traffic": traffic, "peak_source": peak_src, "kernel": "%s<%s,N=%d,mode=%s>" % (lub.kernel_name(n, a.mode, np.float32 if a.dtype == "f32" else np.float64), a.dtype, n, a.mode),
                 "algorithmic_bytes_per_launch": abytes, "avg_launch_ms": avg_ms,
                 "frac_of_8TBps_nominal": achieved / 8000.0,
                 "gflops_2n3": 2.0 * n ** 3 * batch / (avg_ms * 1e-3) / 1e9}

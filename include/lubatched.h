@@ -91,6 +91,12 @@ int lu_batched_geometry(int n, int64_t batch, int pivot_mode, int dtype, int* th
                         int* threads_per_matrix, int* matrices_per_block, int64_t* num_blocks,
                         int* dyn_smem_bytes);
 
+/* Name of the CUDA kernel family the library launches for this configuration on a 16-byte
+ * aligned batch ("lub_tma_kernel", "lub_v3_kernel", "lub_v4_kernel"); for profilers and bench
+ * reports (the reference has one kernel, batched_lu_subwarp, parallel_pivot/luBatchedInplace.cuh:70).
+ * Static string; NULL on bad arguments. */
+const char* lu_batched_kernel_name(int n, int pivot_mode, int dtype);
+
 /* Event-timed kernel time of the most recent lu_batched_inplace* call on this thread, in
  * milliseconds, kernel only (the reference's "Kernel execution time",
  * templated/luBatchedInplace.cu:71-82).  Timing is recorded only after

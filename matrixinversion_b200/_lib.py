@@ -52,6 +52,7 @@ SIGNATURES = {
     "lu_batched_inplace_host": (ctypes.c_int, [_P, _P, ctypes.c_int, ctypes.c_int64, ctypes.c_int, ctypes.c_int]),
     "lu_batched_set_threads": (ctypes.c_int, [ctypes.c_int]),
     "lu_batched_get_threads": (ctypes.c_int, [ctypes.c_int, ctypes.c_int]),
+    "lu_batched_kernel_name": (ctypes.c_char_p, [ctypes.c_int, ctypes.c_int, ctypes.c_int]),
     "lu_batched_geometry": (ctypes.c_int, [ctypes.c_int, ctypes.c_int64, ctypes.c_int, ctypes.c_int, _IP, _IP, _IP, _I64P, _IP]),
     "lu_batched_enable_timing": (ctypes.c_int, [ctypes.c_int]),
     "lu_batched_last_kernel_ms": (ctypes.c_float, []),

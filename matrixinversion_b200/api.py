@@ -140,6 +140,14 @@ def geometry(n: int, batch: int, pivot_mode="parallel", dtype=np.float32) -> Geo
     return Geometry(tpb.value, tpm.value, mpb.value, nb.value, smem.value)
 
 
+def kernel_name(n: int, pivot_mode="parallel", dtype=np.float32) -> str:
+    """Kernel family launched for this configuration (profilers, bench reports)."""
+    s = _lib.lib().lu_batched_kernel_name(n, _mode(pivot_mode), _dtype_code(dtype))
+    if s is None:
+        raise _lib.LubError(-1, "bad configuration")
+    return s.decode()
+
+
 def enable_timing(on: bool = True) -> None:
     check(_lib.lib().lu_batched_enable_timing(int(on)))
 

@@ -21,6 +21,7 @@ struct LaunchInfo {
     int dyn_smem_bytes;
     int regs_per_thread;
     int blocks_per_sm;
+    const char* kernel;
 };
 
 // int launcher(A, piv, batch, threads (0 = default), stream, info (may be NULL), dry_run)
@@ -155,7 +156,7 @@ cudaError_t launch(void* A, int32_t* piv, long long batch, int threads, cudaStre
         if (fast) {
             using TL = TmaLayout<T, N, VC::GR, VC::GC, MODE>;
             constexpr bool BS = (MODE != kModeNone);  // per-tile block barrier: pays only with the pivot search
-            auto kern = lub_tma_kernel<T, N, VC::GR, VC::GC, MODE, VC::MINB, BS>;
+            auto kern = lub_tma_kernel<T, N, VC::GR, VC::GC, MODE, VC::MINB, BS, MODE == kModeNone>;
             smem = TL::smem_bytes(warps); mpw = TL::MPW; g = TL::G; c = &cache_fast[dev];
             err = prepare(kern, *c, dev, threads, smem);
             if (err != cudaSuccess) return err;
@@ -166,7 +167,7 @@ cudaError_t launch(void* A, int32_t* piv, long long batch, int threads, cudaStre
             if (info) {
                 info->threads_per_block = threads; info->threads_per_matrix = g; info->matrices_per_block = warps * mpw;
                 info->num_blocks = blocks; info->dyn_smem_bytes = smem; info->regs_per_thread = c->regs;
-                info->blocks_per_sm = c->blocks_per_sm;
+                info->blocks_per_sm = c->blocks_per_sm; info->kernel = "lub_tma_kernel";
             }
             if (dry_run || batch == 0) return cudaSuccess;
             CUtensorMap map;
@@ -210,6 +211,7 @@ cudaError_t launch(void* A, int32_t* piv, long long batch, int threads, cudaStre
         info->dyn_smem_bytes = smem;
         info->regs_per_thread = c->regs;
         info->blocks_per_sm = c->blocks_per_sm;
+        info->kernel = !fast ? "lub_invert_kernel" : (USE_V4 ? "lub_v4_kernel" : "lub_v3_kernel");
     }
     if (dry_run || batch == 0) return cudaSuccess;
     if (fast) {

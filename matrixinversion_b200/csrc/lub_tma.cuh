@@ -165,9 +165,15 @@ __device__ __forceinline__ void prepass_rowwise_swz(const unsigned char* img0, i
 }
 
 // One warp = one tile of MPW matrices; persistent over tiles.  BSYNC as in lub_v3_kernel.
-template <typename T, int N, int GR, int GC, int MODE, int MINB = 2, bool BSYNC = true>
+// PF (no-pivot mode only): the image is free once the registers are loaded, so the next tile is
+// requested right then, in place, and lands while this one is eliminated (+2.5 %).  The same idea
+// for the pivot modes -- results leaving through two alternating 2 KB output slices -- measured
+// 8 % SLOWER on N = 32 fp32 (profiles/r01_tune_tma.jsonl, "bs3"): the kernel is bound by issue slots
+// and the LSU pipe, not by the wait for its input, so that variant is not kept.
+template <typename T, int N, int GR, int GC, int MODE, int MINB = 2, bool BSYNC = true, bool PF = false>
 __global__ void __launch_bounds__(kMaxThreads, MINB)
 lub_tma_kernel(const __grid_constant__ CUtensorMap tmap, T* __restrict__ A, int32_t* __restrict__ piv, long long batch) {
+    static_assert(!PF || MODE == kModeNone, "in-place prefetch: the pivot modes need the image for the column scatter");
     using L = TmaLayout<T, N, GR, GC, MODE>;
     constexpr int G = L::G, MPW = L::MPW, LR = L::LR, LC = L::LC, CH = L::CH, CPL = L::CPL;
     constexpr int RB = L::RB, ES = L::ES, MAT = L::MAT_BYTES;
@@ -197,6 +203,14 @@ lub_tma_kernel(const __grid_constant__ CUtensorMap tmap, T* __restrict__ A, int3
     unsigned parity = 0;
 
     const long long ntiles = (batch + MPW - 1) / MPW;
+    const long long tstride = (long long)gridDim.x * nwarps;
+    if (PF && lane == 0) {
+        const long long t0 = (long long)blockIdx.x * nwarps + warp;
+        if (t0 < ntiles) {
+            mbar_expect_tx(bar, (unsigned)L::IMG_BYTES);
+            tma_load_3d(img, &tmap, bar, 0, 0, (int)(t0 * MPW));
+        }
+    }
 #pragma unroll 1
     for (long long tbase = (long long)blockIdx.x * nwarps; tbase < ntiles; tbase += (long long)gridDim.x * nwarps) {
         if (BSYNC) __syncthreads();
@@ -207,7 +221,7 @@ lub_tma_kernel(const __grid_constant__ CUtensorMap tmap, T* __restrict__ A, int3
         T* gspan = A + first * (long long)(N * N);
 
         // ---- HBM -> swizzled image, by the TMA unit (matrices past the batch end read as zero) ----
-        if (lane == 0) {
+        if (!PF && lane == 0) {
             if (MODE != kModeNone) tma_store_wait_read();  // last round's tile has left the image
             mbar_expect_tx(bar, (unsigned)L::IMG_BYTES);
             tma_load_3d(img, &tmap, bar, 0, 0, (int)first);
@@ -243,6 +257,15 @@ lub_tma_kernel(const __grid_constant__ CUtensorMap tmap, T* __restrict__ A, int3
 #pragma unroll
                     for (int w = 0; w < CH; ++w) a[li][q * CH + w] = T(0);
                 }
+            }
+        }
+
+        if (PF) {
+            __syncwarp();  // every lane has its block: the image can take the next tile
+            const long long nxt = tile + tstride;
+            if (lane == 0 && nxt < ntiles) {
+                mbar_expect_tx(bar, (unsigned)L::IMG_BYTES);
+                tma_load_3d(img, &tmap, bar, 0, 0, (int)(nxt * MPW));
             }
         }
 

@@ -228,6 +228,12 @@ int lu_batched_geometry(int n, int64_t batch, int pivot_mode, int dtype, int* th
     return LUB_OK;
 }
 
+const char* lu_batched_kernel_name(int n, int pivot_mode, int dtype) {
+    lub::LaunchInfo info{};
+    if (launch_on(nullptr, nullptr, n, 1, pivot_mode, dtype, nullptr, &info, 1) != LUB_OK) return nullptr;
+    return info.kernel;
+}
+
 int lu_batched_inplace_host(void* host_ptr, int32_t* host_piv, int n, int64_t batch, int pivot_mode, int dtype) {
     int rc = check_args(n, batch, pivot_mode, dtype);
     if (rc != LUB_OK) return rc;

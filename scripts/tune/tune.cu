@@ -71,17 +71,17 @@ struct V5 {
 template <typename T, int N, int GR, int GC, int MODE, int MINB, int BS>
 struct VT {
     using L = TmaLayout<T, N, GR, GC, MODE>;
-    static void set_attr(int smem) {
-        cudaFuncSetAttribute(lub_tma_kernel<T, N, GR, GC, MODE, MINB, BS != 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    }
+    static constexpr bool PF = (BS & 2) != 0;
+    static constexpr auto kern() { return lub_tma_kernel<T, N, GR, GC, MODE, MINB, (BS & 1) != 0, PF>; }
+    static void set_attr(int smem) { cudaFuncSetAttribute(kern(), cudaFuncAttributeMaxDynamicSharedMemorySize, smem); }
     static void launch(void* A, int* piv, long long batch, unsigned blocks, int threads, int smem, cudaStream_t s) {
         CUtensorMap map;
         if (make_batch_tmap<T>(&map, A, N, batch, L::MPW) != cudaSuccess) { printf("tensor map failed\n"); return; }
-        lub_tma_kernel<T, N, GR, GC, MODE, MINB, BS != 0><<<blocks, threads, smem, s>>>(map, (T*)A, piv, batch);
+        kern()<<<blocks, threads, smem, s>>>(map, (T*)A, piv, batch);
     }
     static int occ(int threads, int smem) {
         int o = 0;
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, lub_tma_kernel<T, N, GR, GC, MODE, MINB, BS != 0>, threads, smem);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, kern(), threads, smem);
         return o;
     }
     static Variant make(const char* name) { return Variant{name, L::MPW, -1000000, 0, set_attr, launch, occ, &L::smem_bytes}; }
