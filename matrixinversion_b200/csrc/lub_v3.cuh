@@ -175,7 +175,12 @@ __device__ __forceinline__ void copy_out_gather(T* __restrict__ dst, const T* __
 // In-register Gauss-Jordan on the LR x LC block of every lane: row k and column k travel by
 // shuffles, rows are scaled by 1/pivot only at the end (dinv), column k is overwritten with the
 // multipliers as it is cleared (in-place inverse).  Shared by lub_v3_kernel and lub_tma_kernel.
-template <typename T, int N, int GR, int GC, int CH, int CPL, int LR, int LC>
+// XDBG (tuning harness only, wrong results): 4 = no shuffles (lanes use their own registers),
+// 8 = no rank-1 update.
+// (Tried and dropped: doing the lane-dependent fix-ups with 0/1 masks on the FMA pipe instead of selects --
+// bit-identical results, but the compiler rebuilds the FFMA2 register pairs with extra MOVs and the
+// kernel gets 4 % slower, profiles/r01_tune_v6.md.)
+template <typename T, int N, int GR, int GC, int CH, int CPL, int LR, int LC, int XDBG = 0>
 __device__ __forceinline__ void gj_eliminate(T (&a)[LR][LC], T (&dinv)[LR], int gr, int gc, int grp_base) {
     constexpr int G = GR * GC;
 #pragma unroll
@@ -187,12 +192,12 @@ __device__ __forceinline__ void gj_eliminate(T (&a)[LR][LC], T (&dinv)[LR], int 
         T r[LC], c[LR];
 #pragma unroll
         for (int lj = 0; lj < LC; ++lj)
-            r[lj] = (GR > 1) ? shfl_t(a[lk][lj], grp_base + gro * GC + gc) : a[lk][lj];
+            r[lj] = (GR > 1 && !(XDBG & 4)) ? shfl_t(a[lk][lj], grp_base + gro * GC + gc) : a[lk][lj];
 #pragma unroll
         for (int li = 0; li < LR; ++li)
-            c[li] = (GC > 1) ? shfl_t(a[li][ck], grp_base + gr * GC + gco) : a[li][ck];
+            c[li] = (GC > 1 && !(XDBG & 4)) ? shfl_t(a[li][ck], grp_base + gr * GC + gco) : a[li][ck];
         // straight from the owner (not via r[ck]): all shuffles of a step leave in one batch
-        const T pv = (G > 1) ? shfl_t(a[lk][ck], grp_base + gro * GC + gco) : a[lk][ck];
+        const T pv = (G > 1 && !(XDBG & 4)) ? shfl_t(a[lk][ck], grp_base + gro * GC + gco) : a[lk][ck];
         const T rinv = rcp_t(pv);
         set_if(own_col, r[ck], T(1));
         T nf[LR];
@@ -203,7 +208,10 @@ __device__ __forceinline__ void gj_eliminate(T (&a)[LR][LC], T (&dinv)[LR], int 
 #pragma unroll
         for (int li = 0; li < LR; ++li) set_if(own_col, a[li][ck], (li == lk) ? diag : T(0));
 #pragma unroll
-        for (int li = 0; li < LR; ++li) row_update<LC>(a[li], r, nf[li]);
+        for (int li = 0; li < LR; ++li) {
+            if (!(XDBG & 8)) row_update<LC>(a[li], r, nf[li]);
+            else a[li][(li + k) % LC] += nf[li] * r[(li * 3 + k) % LC];  // keeps every value live
+        }
         set_if(own_row, dinv[lk], rinv);
     }
 }

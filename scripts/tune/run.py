@@ -13,7 +13,7 @@ ap.add_argument("--threads", default="128")
 ap.add_argument("--iters", type=int, default=4)
 ap.add_argument("--only", default="")
 a = ap.parse_args()
-T = ctypes.CDLL(os.path.join(os.path.dirname(os.path.abspath(__file__)), "libtune.so"))
+T = ctypes.CDLL(os.path.join(os.path.dirname(os.path.abspath(__file__)), os.environ.get("TUNE_LIB", "libtune.so")))
 T.tune_name.restype = ctypes.c_char_p
 T.tune_launch.argtypes = [ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_longlong, ctypes.c_int, ctypes.c_void_p,
                           ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_int)]

@@ -4,6 +4,7 @@
 #include <cstdio>
 #include "../../matrixinversion_b200/csrc/lub_v5.cuh"
 #include "../../matrixinversion_b200/csrc/lub_tma.cuh"
+#include "../../matrixinversion_b200/csrc/lub_v6.cuh"
 
 using namespace lub;
 
@@ -87,6 +88,26 @@ struct VT {
     static Variant make(const char* name) { return Variant{name, L::MPW, -1000000, 0, set_attr, launch, occ, &L::smem_bytes}; }
 };
 #define VART(T, N, GR, GC, MODE, MINB, BS) VT<T, N, GR, GC, MODE, MINB, BS>::make(#T " N=" #N " " #GR "x" #GC " mode" #MODE " minb" #MINB " bs" #BS " tma")
+
+// warp-specialised TMA kernel: one persistent block per SM; warp_bytes == -2000000 marks it
+template <typename T, int N, int GR, int GC, int MODE, int NCW, int NPW, int NB, int CREG, int PREG, int NCG, int LA, int DBG>
+struct VT6 {
+    using L = V6Layout<T, N, GR, GC, MODE, NB>;
+    static constexpr auto kern() { return lub_v6_kernel<T, N, GR, GC, MODE, NCW, NPW, NB, CREG, PREG, NCG, LA, DBG>; }
+    static void set_attr(int smem) { cudaFuncSetAttribute(kern(), cudaFuncAttributeMaxDynamicSharedMemorySize, smem); }
+    static void launch(void* A, int* piv, long long batch, unsigned blocks, int threads, int smem, cudaStream_t s) {
+        CUtensorMap map;
+        if (make_batch_tmap<T>(&map, A, N, batch, L::MPW) != cudaSuccess) { printf("tensor map failed\n"); return; }
+        kern()<<<blocks, threads, smem, s>>>(map, (T*)A, piv, batch);
+    }
+    static int occ(int threads, int smem) {
+        int o = 0;
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, kern(), threads, smem);
+        return o;
+    }
+    static Variant make(const char* name) { return Variant{name, L::MPW, -(NCW + NPW) * 32, L::SMEM_BYTES, set_attr, launch, occ}; }
+};
+#define VART6(T, N, GR, GC, MODE, NCW, NPW, NB, CREG, PREG, NCG, LA, DBG) VT6<T, N, GR, GC, MODE, NCW, NPW, NB, CREG, PREG, NCG, LA, DBG>::make(#T " N=" #N " " #GR "x" #GC " mode" #MODE " c" #NCW " p" #NPW " nb" #NB " creg" #CREG " preg" #PREG " ncg" #NCG " la" #LA " dbg" #DBG " v6")
 
 #define VAR5(T, N, GR, GC, MODE, NPW, NCW, NB, PRE) V5<T, N, GR, GC, MODE, NPW, NCW, NB, PRE>::make(#T " N=" #N " " #GR "x" #GC " mode" #MODE " p" #NPW " c" #NCW " nb" #NB " opt" #PRE " v5")
 
