@@ -120,8 +120,30 @@ __device__ __noinline__ void prepass_exact_swz(const unsigned char* mimg, int* p
     }
 }
 
+// warp-wide max |v| of a float in ONE instruction (CREDUX.MAXABS.F32, sm_100a); NaNs are ignored
+__device__ __forceinline__ float warp_max_abs(float v) {
+    float r;
+    asm volatile("redux.sync.max.abs.f32 %0, %1, 0xffffffff;" : "=f"(r) : "f"(v));
+    return r;
+}
+
+#ifndef LUB_PREPASS_F32
+#define LUB_PREPASS_F32 1
+#endif
+
 // Row-wise pivot search (see prepass_rowwise in lub_fast.cuh) on the swizzled image: lane = original
 // row, one LDS.128 per 16-byte chunk of the row, conflict-free because of the swizzle.
+//
+// fp32 runs the search in floating point on the FMA pipe: on B200 every 16-lane ALU-pipe instruction
+// (LOP3, SHF, ISETP, SEL) holds the scheduler's dispatch port for two cycles and an FFMA/FMUL for one
+// (profiles/r01_tune_v6.md), and the integer form is five ALU instructions per step.  Here a step is
+//   v = x * alive (FMUL)  ->  m = max |v| over the warp (CREDUX.MAXABS.F32)  ->  hit = (|v| == m) as 1.0/0.0 (FSET)
+//   ->  when += hit * k (FFMA)  ->  alive -= hit * alive (FFMA)
+// with alive in {1.0, 0.0}; every operation is exact.  The comparisons are the reference's
+// (fabs(a) > fabs(b) on the un-eliminated entries, serial_pivot/luBatchedInplace.cuh:24-41).  A step whose
+// maximum is shared (equal |values|, or an all-zero remaining column, where retired lanes "hit" as well)
+// retires several lanes at once, the survivors then do not add up to one and the matrix is redone
+// by the exact search -- the same rule as the integer form.
 template <typename T, int N, int MODE, int MI>
 __device__ __forceinline__ void prepass_rowwise_swz(const unsigned char* img0, int* perm0, const int8_t* slot_rank, int lane) {
     using U = typename FpBits<T>::U;
@@ -129,37 +151,71 @@ __device__ __forceinline__ void prepass_rowwise_swz(const unsigned char* img0, i
     const int row = (lane < N) ? lane : 0;
     const unsigned char* rowp = img0 + row * RB;
     const int xr = (row & 7) << 4;
-    U alive[MI];
-    int when[MI];
-#pragma unroll
-    for (int m = 0; m < MI; ++m) { alive[m] = (lane < N) ? ~U(0) : U(0); when[m] = N - 1; }
     T x[MI][EPV];
+    if constexpr (sizeof(T) == 4 && (LUB_PREPASS_F32 != 0)) {
+        float alive[MI], when[MI];
 #pragma unroll
-    for (int k = 0; k < N - 1; ++k) {
-        if ((k % EPV) == 0) {
+        for (int m = 0; m < MI; ++m) { alive[m] = (lane < N) ? 1.0f : 0.0f; when[m] = 0.0f; }
 #pragma unroll
-            for (int m = 0; m < MI; ++m)
-                ld_vec<T, EPV>(reinterpret_cast<const T*>(rowp + m * MAT + (((k / EPV) << 4) ^ xr)), x[m]);
+        for (int k = 0; k < N - 1; ++k) {
+            if ((k % EPV) == 0) {
+#pragma unroll
+                for (int m = 0; m < MI; ++m)
+                    ld_vec<T, EPV>(reinterpret_cast<const T*>(rowp + m * MAT + (((k / EPV) << 4) ^ xr)), x[m]);
+            }
+            float v[MI], mx[MI];
+#pragma unroll
+            for (int m = 0; m < MI; ++m) v[m] = x[m][k % EPV] * alive[m];
+#pragma unroll
+            for (int m = 0; m < MI; ++m) mx[m] = warp_max_abs(v[m]);
+#pragma unroll
+            for (int m = 0; m < MI; ++m) {
+                const float hit = (fabsf(v[m]) == mx[m]) ? 1.0f : 0.0f;
+                when[m] = fmaf(hit, (float)k, when[m]);
+                alive[m] = fmaf(-hit, alive[m], alive[m]);
+            }
         }
-        U key[MI], mx[MI];
-#pragma unroll
-        for (int m = 0; m < MI; ++m) key[m] = ((FpBits<T>::absbits(x[m][k % EPV]) << 1) | U(1)) & alive[m];
-#pragma unroll
-        for (int m = 0; m < MI; ++m) mx[m] = warp_max_bits(key[m]);
 #pragma unroll
         for (int m = 0; m < MI; ++m) {
-            const bool hit = key[m] == mx[m];
-            when[m] = hit ? k : when[m];
-            alive[m] = hit ? U(0) : alive[m];
+            const bool ok = __popc(__ballot_sync(0xffffffffu, alive[m] != 0.0f)) == 1;  // warp-uniform
+            if (ok) {
+                if (lane < N) perm0[m * N + ((alive[m] != 0.0f) ? (N - 1) : (int)when[m])] = lane;
+            } else {
+                prepass_exact_swz<T, N, MODE>(img0 + m * MAT, perm0 + m * N, slot_rank, lane);
+            }
         }
-    }
+    } else {
+        U alive[MI];
+        int when[MI];
 #pragma unroll
-    for (int m = 0; m < MI; ++m) {
-        const bool ok = __popc(__ballot_sync(0xffffffffu, alive[m] != U(0))) == 1;  // warp-uniform
-        if (ok) {
-            if (lane < N) perm0[m * N + when[m]] = lane;
-        } else {
-            prepass_exact_swz<T, N, MODE>(img0 + m * MAT, perm0 + m * N, slot_rank, lane);
+        for (int m = 0; m < MI; ++m) { alive[m] = (lane < N) ? ~U(0) : U(0); when[m] = N - 1; }
+#pragma unroll
+        for (int k = 0; k < N - 1; ++k) {
+            if ((k % EPV) == 0) {
+#pragma unroll
+                for (int m = 0; m < MI; ++m)
+                    ld_vec<T, EPV>(reinterpret_cast<const T*>(rowp + m * MAT + (((k / EPV) << 4) ^ xr)), x[m]);
+            }
+            U key[MI], mx[MI];
+#pragma unroll
+            for (int m = 0; m < MI; ++m) key[m] = ((FpBits<T>::absbits(x[m][k % EPV]) << 1) | U(1)) & alive[m];
+#pragma unroll
+            for (int m = 0; m < MI; ++m) mx[m] = warp_max_bits(key[m]);
+#pragma unroll
+            for (int m = 0; m < MI; ++m) {
+                const bool hit = key[m] == mx[m];
+                when[m] = hit ? k : when[m];
+                alive[m] = hit ? U(0) : alive[m];
+            }
+        }
+#pragma unroll
+        for (int m = 0; m < MI; ++m) {
+            const bool ok = __popc(__ballot_sync(0xffffffffu, alive[m] != U(0))) == 1;  // warp-uniform
+            if (ok) {
+                if (lane < N) perm0[m * N + when[m]] = lane;
+            } else {
+                prepass_exact_swz<T, N, MODE>(img0 + m * MAT, perm0 + m * N, slot_rank, lane);
+            }
         }
     }
 }
