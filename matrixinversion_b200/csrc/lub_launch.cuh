@@ -150,13 +150,18 @@ cudaError_t launch(void* A, int32_t* piv, long long batch, int threads, cudaStre
     static KernelCache cache_fast[kMaxDevices] = {}, cache_gen[kMaxDevices] = {};
     int smem, mpw, g;
     KernelCache* c;
-    // rows of exactly 128 bytes (N = 32 fp32, N = 16 fp64): the TMA-staged kernel (lub_tma.cuh)
-    constexpr bool USE_TMA = kUseTma && (N * sizeof(T) == 128) && TmaOk<T, N, VC::GR, VC::GC>::value;
+    // rows of one 128-byte line (N = 32 fp32, N = 16 fp64): the TMA-staged kernel (lub_tma.cuh) in every
+    // mode; rows of two lines (N = 32 fp64): in the pivot modes only -- without pivoting the rolled-step
+    // kernel (lub_v4.cuh) is still ahead there (profiles/r01_tune_late.jsonl)
+    constexpr int ROWB = N * (int)sizeof(T);
+    constexpr bool USE_TMA = kUseTma && (ROWB == 128 || (ROWB == 256 && MODE != kModeNone)) && TmaOk<T, N, VC::GR, VC::GC>::value;
     if constexpr (USE_TMA) {
         if (fast) {
             using TL = TmaLayout<T, N, VC::GR, VC::GC, MODE>;
-            constexpr bool BS = (MODE != kModeNone);  // per-tile block barrier: pays only with the pivot search
-            auto kern = lub_tma_kernel<T, N, VC::GR, VC::GC, MODE, VC::MINB, BS, MODE == kModeNone>;
+            // pivot modes: per-tile block barrier (pays with the pivot search).  No pivoting: no barrier,
+            // results leave through the image and a bulk store (5-18 % faster than register stores + in-place prefetch)
+            constexpr bool BS = (MODE != kModeNone);
+            auto kern = lub_tma_kernel<T, N, VC::GR, VC::GC, MODE, VC::MINB, BS, false, MODE == kModeNone>;
             smem = TL::smem_bytes(warps); mpw = TL::MPW; g = TL::G; c = &cache_fast[dev];
             err = prepare(kern, *c, dev, threads, smem);
             if (err != cudaSuccess) return err;

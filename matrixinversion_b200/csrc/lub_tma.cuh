@@ -1,6 +1,7 @@
 // lub_tma.cuh -- TMA-staged variant of the in-register Gauss-Jordan kernel (lub_v3.cuh) for the
-// sizes whose rows are exactly one 128-byte line (N = 32 fp32 -- the headline configuration of
-// parallel_pivot/luBatchedInplace.cu -- and N = 16 fp64).
+// sizes whose rows are whole 128-byte lines: N = 32 fp32 (the headline configuration of
+// parallel_pivot/luBatchedInplace.cu) and N = 16 fp64 (one line per row), N = 32 fp64 (two lines
+// per row, BASELINE config 5).
 //
 // Why: lub_v3_kernel is bound by the LSU pipe (shared-memory wavefronts + shuffles + LDG/STG,
 // profiles/r01_prof_headline_*.md: ~616 wavefronts per matrix, 66 % of the pipe's peak).  About a
@@ -46,6 +47,25 @@ __device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, const void*
     asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
                  ::"l"(map), "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2) : "memory");
 }
+__device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* map, void* bar, int c0, int c1, int c2, int c3) {
+    asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+                 ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, const void* src, int c0, int c1, int c2, int c3) {
+    asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+                 ::"l"(map), "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+// one warp tile (MPW whole matrices starting at matrix `first`); LPR = 128-byte lines per row
+template <int LPR>
+__device__ __forceinline__ void tma_load_tile(void* dst, const CUtensorMap* map, void* bar, int first) {
+    if (LPR == 1) tma_load_3d(dst, map, bar, 0, 0, first);
+    else tma_load_4d(dst, map, bar, 0, 0, 0, first);
+}
+template <int LPR>
+__device__ __forceinline__ void tma_store_tile(const CUtensorMap* map, const void* src, int first) {
+    if (LPR == 1) tma_store_3d(map, src, 0, 0, first);
+    else tma_store_4d(map, src, 0, 0, 0, first);
+}
 __device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
@@ -56,7 +76,8 @@ struct TmaLayout {
     static constexpr int ES = sizeof(T);
     static constexpr int EPV = 16 / ES;
     static constexpr int RB = N * ES;  // row bytes
-    static_assert(RB == 128, "one row = one 128-byte swizzle line");
+    static_assert(RB % 128 == 0, "a row is a whole number of 128-byte swizzle lines");
+    static constexpr int LPR = RB / 128;  // lines per row
     static constexpr int G = GR * GC;
     static_assert(G >= 1 && G <= 32 && (32 % G) == 0, "G must divide 32");
     static constexpr int MPW = 32 / G;
@@ -76,9 +97,17 @@ struct TmaLayout {
     }
 };
 
-// byte offset of element (row, col) inside one matrix of the swizzled image
+// byte offset, inside one matrix of the swizzled image, of byte b (< RB) of row `row`: the 16-byte
+// chunk index within a 128-byte line is XORed with the line index mod 8 (matrices are 1 KB multiples)
+template <int RB>
+__device__ __forceinline__ int swz_byte(int row, int b) {
+    if (RB == 128) return row * 128 + (b ^ ((row & 7) << 4));
+    const int o = row * RB + b;
+    return o ^ (((o >> 7) & 7) << 4);
+}
+// byte offset of element (row, col)
 template <int RB, int ES>
-__device__ __forceinline__ int swz_off(int row, int col) { return row * RB + ((col * ES) ^ ((row & 7) << 4)); }
+__device__ __forceinline__ int swz_off(int row, int col) { return swz_byte<RB>(row, col * ES); }
 
 // Exact warp-wide pivot search on the swizzled image (explicit tree priorities): the rare path for
 // matrices with equal |values| in one column.  Same search as prepass_group (lub_fast.cuh).
@@ -149,8 +178,6 @@ __device__ __forceinline__ void prepass_rowwise_swz(const unsigned char* img0, i
     using U = typename FpBits<T>::U;
     constexpr int ES = sizeof(T), EPV = 16 / ES, RB = N * ES, MAT = N * RB;
     const int row = (lane < N) ? lane : 0;
-    const unsigned char* rowp = img0 + row * RB;
-    const int xr = (row & 7) << 4;
     T x[MI][EPV];
     if constexpr (sizeof(T) == 4 && (LUB_PREPASS_F32 != 0)) {
         float alive[MI], when[MI];
@@ -161,7 +188,7 @@ __device__ __forceinline__ void prepass_rowwise_swz(const unsigned char* img0, i
             if ((k % EPV) == 0) {
 #pragma unroll
                 for (int m = 0; m < MI; ++m)
-                    ld_vec<T, EPV>(reinterpret_cast<const T*>(rowp + m * MAT + (((k / EPV) << 4) ^ xr)), x[m]);
+                    ld_vec<T, EPV>(reinterpret_cast<const T*>(img0 + m * MAT + swz_byte<RB>(row, (k / EPV) << 4)), x[m]);
             }
             float v[MI], mx[MI];
 #pragma unroll
@@ -194,7 +221,7 @@ __device__ __forceinline__ void prepass_rowwise_swz(const unsigned char* img0, i
             if ((k % EPV) == 0) {
 #pragma unroll
                 for (int m = 0; m < MI; ++m)
-                    ld_vec<T, EPV>(reinterpret_cast<const T*>(rowp + m * MAT + (((k / EPV) << 4) ^ xr)), x[m]);
+                    ld_vec<T, EPV>(reinterpret_cast<const T*>(img0 + m * MAT + swz_byte<RB>(row, (k / EPV) << 4)), x[m]);
             }
             U key[MI], mx[MI];
 #pragma unroll
@@ -226,10 +253,14 @@ __device__ __forceinline__ void prepass_rowwise_swz(const unsigned char* img0, i
 // for the pivot modes -- results leaving through two alternating 2 KB output slices -- measured
 // 8 % SLOWER on N = 32 fp32 (profiles/r01_tune_tma.jsonl, "bs3"): the kernel is bound by issue slots
 // and the LSU pipe, not by the wait for its input, so that variant is not kept.
-template <typename T, int N, int GR, int GC, int MODE, int MINB = 2, bool BSYNC = true, bool PF = false>
+// OUTIMG (no-pivot mode only, excludes PF): the results leave like in the pivot modes -- 16-byte vector
+// stores into the swizzled image, then one bulk tensor store -- instead of straight from the registers.
+template <typename T, int N, int GR, int GC, int MODE, int MINB = 2, bool BSYNC = true, bool PF = false, bool OUTIMG = false>
 __global__ void __launch_bounds__(kMaxThreads, MINB)
 lub_tma_kernel(const __grid_constant__ CUtensorMap tmap, T* __restrict__ A, int32_t* __restrict__ piv, long long batch) {
     static_assert(!PF || MODE == kModeNone, "in-place prefetch: the pivot modes need the image for the column scatter");
+    static_assert(!OUTIMG || (MODE == kModeNone && !PF), "OUTIMG is the no-pivot output path without in-place prefetch");
+    constexpr bool VIA_IMG = (MODE != kModeNone) || OUTIMG;  // results go through the image and a bulk store
     using L = TmaLayout<T, N, GR, GC, MODE>;
     constexpr int G = L::G, MPW = L::MPW, LR = L::LR, LC = L::LC, CH = L::CH, CPL = L::CPL;
     constexpr int RB = L::RB, ES = L::ES, MAT = L::MAT_BYTES;
@@ -264,7 +295,7 @@ lub_tma_kernel(const __grid_constant__ CUtensorMap tmap, T* __restrict__ A, int3
         const long long t0 = (long long)blockIdx.x * nwarps + warp;
         if (t0 < ntiles) {
             mbar_expect_tx(bar, (unsigned)L::IMG_BYTES);
-            tma_load_3d(img, &tmap, bar, 0, 0, (int)(t0 * MPW));
+            tma_load_tile<L::LPR>(img, &tmap, bar, (int)(t0 * MPW));
         }
     }
 #pragma unroll 1
@@ -278,9 +309,9 @@ lub_tma_kernel(const __grid_constant__ CUtensorMap tmap, T* __restrict__ A, int3
 
         // ---- HBM -> swizzled image, by the TMA unit (matrices past the batch end read as zero) ----
         if (!PF && lane == 0) {
-            if (MODE != kModeNone) tma_store_wait_read();  // last round's tile has left the image
+            if (VIA_IMG) tma_store_wait_read();  // last round's tile has left the image
             mbar_expect_tx(bar, (unsigned)L::IMG_BYTES);
-            tma_load_3d(img, &tmap, bar, 0, 0, (int)first);
+            tma_load_tile<L::LPR>(img, &tmap, bar, (int)first);
         }
         mbar_wait(bar, parity);
         parity ^= 1u;
@@ -303,12 +334,10 @@ lub_tma_kernel(const __grid_constant__ CUtensorMap tmap, T* __restrict__ A, int3
             const bool rok = (li * GR + GR - 1 < N) || (i < N);
             int prow = rok ? i : 0;
             if (MODE != kModeNone) prow = rok ? perm[i] : 0;
-            const unsigned char* rowp = mimg + prow * RB;
-            const int xr = (prow & 7) << 4;
 #pragma unroll
             for (int q = 0; q < CPL; ++q) {
                 if (rok) {
-                    ld_vec<T, CH>(reinterpret_cast<const T*>(rowp + (((gc * CPL + q) << 4) ^ xr)), &a[li][q * CH]);
+                    ld_vec<T, CH>(reinterpret_cast<const T*>(mimg + swz_byte<RB>(prow, (gc * CPL + q) << 4)), &a[li][q * CH]);
                 } else {
 #pragma unroll
                     for (int w = 0; w < CH; ++w) a[li][q * CH + w] = T(0);
@@ -321,7 +350,7 @@ lub_tma_kernel(const __grid_constant__ CUtensorMap tmap, T* __restrict__ A, int3
             const long long nxt = tile + tstride;
             if (lane == 0 && nxt < ntiles) {
                 mbar_expect_tx(bar, (unsigned)L::IMG_BYTES);
-                tma_load_3d(img, &tmap, bar, 0, 0, (int)(nxt * MPW));
+                tma_load_tile<L::LPR>(img, &tmap, bar, (int)(nxt * MPW));
             }
         }
 
@@ -336,7 +365,23 @@ lub_tma_kernel(const __grid_constant__ CUtensorMap tmap, T* __restrict__ A, int3
 #pragma unroll
             for (int lj = 0; lj < LC; ++lj) a[li][lj] *= dinv[li];
         }
-        if (MODE == kModeNone) {
+        if (OUTIMG) {
+            __syncwarp();  // every lane has its block: the image may be overwritten
+#pragma unroll
+            for (int li = 0; li < LR; ++li) {
+                const int i = li * GR + gr;
+                const bool rok = (li * GR + GR - 1 < N) || (i < N);
+#pragma unroll
+                for (int q = 0; q < CPL; ++q)
+                    if (rok) st_vec<T, CH>(reinterpret_cast<T*>(mimg + swz_byte<RB>(i, (gc * CPL + q) << 4)), &a[li][q * CH]);
+            }
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) {
+                tma_store_tile<L::LPR>(&tmap, img, (int)first);
+                tma_store_commit();
+            }
+        } else if (MODE == kModeNone) {
             T* gm = gspan + (size_t)ml * (N * N) + gc * LC;
 #pragma unroll
             for (int li = 0; li < LR; ++li) {
@@ -355,16 +400,14 @@ lub_tma_kernel(const __grid_constant__ CUtensorMap tmap, T* __restrict__ A, int3
             for (int li = 0; li < LR; ++li) {
                 const int i = li * GR + gr;
                 const bool rok = (li * GR + GR - 1 < N) || (i < N);
-                unsigned char* rowp = mimg + i * RB;
-                const int xr = (i & 7) << 4;
 #pragma unroll
                 for (int lj = 0; lj < LC; ++lj)
-                    if (rok) *reinterpret_cast<T*>(rowp + (pcb[lj] ^ xr)) = a[li][lj];
+                    if (rok) *reinterpret_cast<T*>(mimg + swz_byte<RB>(i, pcb[lj])) = a[li][lj];
             }
             fence_proxy_async();  // generic-proxy writes -> visible to the TMA unit
             __syncwarp();
             if (lane == 0) {
-                tma_store_3d(&tmap, img, 0, 0, (int)first);  // rows past the batch end are clipped
+                tma_store_tile<L::LPR>(&tmap, img, (int)first);  // matrices past the batch end are clipped
                 tma_store_commit();
             }
         }
@@ -377,7 +420,7 @@ lub_tma_kernel(const __grid_constant__ CUtensorMap tmap, T* __restrict__ A, int3
         }
         __syncwarp();
     }
-    if (MODE != kModeNone && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // stores complete
+    if (VIA_IMG && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // stores complete
 }
 
 // ---- host: tensor map over the batch viewed as [batch][N][N], box = one warp tile ----------------
@@ -400,13 +443,24 @@ template <typename T>
 inline cudaError_t make_batch_tmap(CUtensorMap* map, void* A, int n, long long batch, int mpw) {
     EncodeTiledFn enc = encode_tiled_fn();
     if (!enc) return cudaErrorNotSupported;
-    const cuuint64_t dims[3] = {(cuuint64_t)n, (cuuint64_t)n, (cuuint64_t)batch};
-    const cuuint64_t strides[2] = {(cuuint64_t)n * sizeof(T), (cuuint64_t)n * n * sizeof(T)};
-    const cuuint32_t box[3] = {(cuuint32_t)n, (cuuint32_t)n, (cuuint32_t)mpw};
-    const cuuint32_t estr[3] = {1, 1, 1};
     const CUtensorMapDataType dt = (sizeof(T) == 4) ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT64;
-    const CUresult r = enc(map, dt, 3, A, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
-                           CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    const cuuint32_t estr[4] = {1, 1, 1, 1};
+    const int row_bytes = n * (int)sizeof(T);
+    CUresult r;
+    if (row_bytes == 128) {  // [batch][n][n], one swizzle line per row
+        const cuuint64_t dims[3] = {(cuuint64_t)n, (cuuint64_t)n, (cuuint64_t)batch};
+        const cuuint64_t strides[2] = {(cuuint64_t)row_bytes, (cuuint64_t)n * row_bytes};
+        const cuuint32_t box[3] = {(cuuint32_t)n, (cuuint32_t)n, (cuuint32_t)mpw};
+        r = enc(map, dt, 3, A, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    } else {  // rows of several lines: [batch][n][lines][128 bytes]; the box is still whole matrices, rows contiguous
+        const int epl = 128 / (int)sizeof(T), lpr = row_bytes / 128;
+        const cuuint64_t dims[4] = {(cuuint64_t)epl, (cuuint64_t)lpr, (cuuint64_t)n, (cuuint64_t)batch};
+        const cuuint64_t strides[3] = {128, (cuuint64_t)row_bytes, (cuuint64_t)n * row_bytes};
+        const cuuint32_t box[4] = {(cuuint32_t)epl, (cuuint32_t)lpr, (cuuint32_t)n, (cuuint32_t)mpw};
+        r = enc(map, dt, 4, A, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    }
     return r == CUDA_SUCCESS ? cudaSuccess : cudaErrorInvalidValue;
 }
 
