@@ -252,8 +252,8 @@ def main():
         if world > 1:
             dist.all_reduce(te, op=dist.ReduceOp.MAX)
         e2e = {"value": world * batch * a.e2e_steps / float(te.item()), "unit": UNIT,
-               "h2d_bytes_per_step": batch * n * n * esize, "d2h_bytes_per_step": batch * n * n * esize,
-               "steps": a.e2e_steps, "api": "matrixinversion_b200.lu_batched_inplace(numpy pinned) -> lu_batched_inplace_host"}
+               "h2d_bytes_per_step": world * batch * n * n * esize, "d2h_bytes_per_step": world * batch * n * n * esize,
+               "bytes_per_step_per_rank": batch * n * n * esize, "steps": a.e2e_steps, "api": "matrixinversion_b200.lu_batched_inplace(numpy pinned) -> lu_batched_inplace_host"}
         del hbuf, H
 
     if rank != 0:
