@@ -100,9 +100,34 @@ struct V3Cfg {
 #define LUB_USE_TMA 1
 #endif
 constexpr bool kUseTma = LUB_USE_TMA != 0;
-// the TMA kernel wants the 16-byte chunks of a row to split evenly over the lane columns
-template <typename T, int N, int GR, int GC>
-struct TmaOk { static constexpr bool value = ((N * (int)sizeof(T) / 16) % GC) == 0 && (32 % (GR * GC)) == 0; };
+
+// Which configurations run the TMA-staged kernel (lub_tma.cuh), on which lane grid and with or without
+// the per-tile block barrier.  Measured choices (profiles/r01_tune_tma.jsonl, r01_tune_late.jsonl):
+//   * rows of one 128-byte line (N = 32 fp32, N = 16 fp64): every mode, the v3 lane grid;
+//   * rows of two lines (N = 32 fp64): pivot modes only -- without pivoting the rolled-step kernel
+//     (lub_v4.cuh) is still ahead;
+//   * fp32 N = 20, 24, 28 (rows zero-padded to one line by the TMA unit): no pivoting and serial pivoting,
+//     plus parallel pivoting at N = 24; elsewhere the position-wise pivot search on the swizzled image
+//     (4-way bank conflicts on its column walk) loses to the odd-stride image of lub_v3.cuh.  Smaller N
+//     would need a padded image too large for two blocks per SM.
+struct TmaChoice { bool on; int gr, gc; bool bsync; };
+constexpr TmaChoice pick_tma(int n, int es, int mode, Cfg v3) {
+    const int rowb = n * es;
+    const bool piv = mode != kModeNone;
+    if (rowb == 128) return TmaChoice{true, v3.gr, v3.gc, piv};
+    if (rowb == 256) return TmaChoice{piv, v3.gr, v3.gc, true};
+    if (es == 4 && n == 20) return TmaChoice{mode != kModeParallel, 4, 2, piv};
+    if (es == 4 && n == 24) return TmaChoice{true, 8, 2, mode == kModeParallel};
+    if (es == 4 && n == 28) return TmaChoice{mode != kModeParallel, 4, 4, false};
+    return TmaChoice{false, v3.gr, v3.gc, false};
+}
+template <typename T, int N, int MODE>
+struct TmaCfg {
+    static constexpr TmaChoice c = pick_tma(N, (int)sizeof(T), MODE, Cfg{V3Cfg<T, N, MODE>::GR, V3Cfg<T, N, MODE>::GC});
+    static constexpr bool ON = kUseTma && c.on;
+    static constexpr int GR = c.gr, GC = c.gc;
+    static constexpr bool BSYNC = c.bsync;
+};
 
 constexpr int kMaxDevices = 64;
 
@@ -150,18 +175,14 @@ cudaError_t launch(void* A, int32_t* piv, long long batch, int threads, cudaStre
     static KernelCache cache_fast[kMaxDevices] = {}, cache_gen[kMaxDevices] = {};
     int smem, mpw, g;
     KernelCache* c;
-    // rows of one 128-byte line (N = 32 fp32, N = 16 fp64): the TMA-staged kernel (lub_tma.cuh) in every
-    // mode; rows of two lines (N = 32 fp64): in the pivot modes only -- without pivoting the rolled-step
-    // kernel (lub_v4.cuh) is still ahead there (profiles/r01_tune_late.jsonl)
-    constexpr int ROWB = N * (int)sizeof(T);
-    constexpr bool USE_TMA = kUseTma && (ROWB == 128 || (ROWB == 256 && MODE != kModeNone)) && TmaOk<T, N, VC::GR, VC::GC>::value;
+    using TC = TmaCfg<T, N, MODE>;
+    constexpr bool USE_TMA = TC::ON;
     if constexpr (USE_TMA) {
         if (fast) {
-            using TL = TmaLayout<T, N, VC::GR, VC::GC, MODE>;
-            // pivot modes: per-tile block barrier (pays with the pivot search).  No pivoting: no barrier,
-            // results leave through the image and a bulk store (5-18 % faster than register stores + in-place prefetch)
-            constexpr bool BS = (MODE != kModeNone);
-            auto kern = lub_tma_kernel<T, N, VC::GR, VC::GC, MODE, VC::MINB, BS, false, MODE == kModeNone>;
+            using TL = TmaLayout<T, N, TC::GR, TC::GC, MODE>;
+            // no pivoting: results leave through the image and a bulk store (5-18 % faster than register
+            // stores + in-place prefetch)
+            auto kern = lub_tma_kernel<T, N, TC::GR, TC::GC, MODE, VC::MINB, TC::BSYNC, false, MODE == kModeNone>;
             smem = TL::smem_bytes(warps); mpw = TL::MPW; g = TL::G; c = &cache_fast[dev];
             err = prepare(kern, *c, dev, threads, smem);
             if (err != cudaSuccess) return err;

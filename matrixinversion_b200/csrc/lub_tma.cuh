@@ -75,16 +75,19 @@ template <typename T, int N, int GR, int GC, int MODE>
 struct TmaLayout {
     static constexpr int ES = sizeof(T);
     static constexpr int EPV = 16 / ES;
-    static constexpr int RB = N * ES;  // row bytes
-    static_assert(RB % 128 == 0, "a row is a whole number of 128-byte swizzle lines");
+    static constexpr int ROWB = N * ES;                    // row bytes in global memory
+    static constexpr int RB = (ROWB + 127) / 128 * 128;    // row pitch of the image: whole 128-byte swizzle lines
+    static constexpr bool PADDED = RB != ROWB;             // N < 32 fp32: the TMA unit zero-fills the rest of the line
+    static_assert(ROWB % 16 == 0, "TMA needs 16-byte multiples as global strides");
+    static_assert(!PADDED || RB == 128, "padding is only done up to one line");
     static constexpr int LPR = RB / 128;  // lines per row
     static constexpr int G = GR * GC;
     static_assert(G >= 1 && G <= 32 && (32 % G) == 0, "G must divide 32");
     static constexpr int MPW = 32 / G;
     static constexpr int CH = EPV;
-    static constexpr int CPR = N / CH;  // 16-byte chunks per row (8)
-    static_assert(CPR % GC == 0, "chunks must split evenly over the lane columns");
-    static constexpr int CPL = CPR / GC;
+    static constexpr int CPR = N / CH;  // 16-byte chunks per row that hold data
+    static constexpr int CPL = (CPR + GC - 1) / GC;  // chunks per lane; a lane may also hold zero-filled padding chunks
+    static_assert(GC * CPL * 16 <= RB, "lanes must stay inside the image row");
     static constexpr int LC = CPL * CH;
     static constexpr int LR = (N + GR - 1) / GR;
     static constexpr int MAT_BYTES = N * RB;
@@ -97,8 +100,9 @@ struct TmaLayout {
     }
 };
 
-// byte offset, inside one matrix of the swizzled image, of byte b (< RB) of row `row`: the 16-byte
-// chunk index within a 128-byte line is XORed with the line index mod 8 (matrices are 1 KB multiples)
+// byte offset, inside the swizzled image of a TILE, of byte b (< RB) of tile row `row` (= matrix in the
+// tile * N + row in the matrix): the 16-byte chunk index within a 128-byte line is XORed with the line
+// index mod 8 (tile images are 1 KB aligned; a matrix inside a tile need not be)
 template <int RB>
 __device__ __forceinline__ int swz_byte(int row, int b) {
     if (RB == 128) return row * 128 + (b ^ ((row & 7) << 4));
@@ -111,14 +115,15 @@ __device__ __forceinline__ int swz_off(int row, int col) { return swz_byte<RB>(r
 
 // Exact warp-wide pivot search on the swizzled image (explicit tree priorities): the rare path for
 // matrices with equal |values| in one column.  Same search as prepass_group (lub_fast.cuh).
+// `img` is the tile image, `row0` the tile row at which this matrix starts.
 template <typename T, int N, int MODE>
-__device__ __noinline__ void prepass_exact_swz(const unsigned char* mimg, int* perm, const int8_t* slot_rank, int lane) {
+__device__ __noinline__ void prepass_exact_swz(const unsigned char* img, int row0, int* perm, const int8_t* slot_rank, int lane) {
     using U = typename FpBits<T>::U;
-    constexpr int RB = N * (int)sizeof(T), ES = sizeof(T);
+    constexpr int ES = sizeof(T), RB = (N * ES + 127) / 128 * 128;
     for (int i = lane; i < N; i += 32) perm[i] = i;
     __syncwarp();
     for (int k = 0; k < N - 1; ++k) {
-        U best_v = FpBits<T>::absbits(*reinterpret_cast<const T*>(mimg + swz_off<RB, ES>(perm[k], k)));
+        U best_v = FpBits<T>::absbits(*reinterpret_cast<const T*>(img + swz_off<RB, ES>(row0 + perm[k], k)));
         unsigned best_p = 0;
         for (int t = lane; t < N - 1 - k; t += 32) {
             int pr;
@@ -128,7 +133,7 @@ __device__ __noinline__ void prepass_exact_swz(const unsigned char* mimg, int* p
             } else {
                 pr = t;
             }
-            const U v = FpBits<T>::absbits(*reinterpret_cast<const T*>(mimg + swz_off<RB, ES>(perm[k + 1 + t], k)));
+            const U v = FpBits<T>::absbits(*reinterpret_cast<const T*>(img + swz_off<RB, ES>(row0 + perm[k + 1 + t], k)));
             const unsigned p = ((unsigned)(pr + 1) << 8) | (unsigned)(t + 1);
             if (v > best_v || (v == best_v && p < best_p)) { best_v = v; best_p = p; }
         }
@@ -173,10 +178,11 @@ __device__ __forceinline__ float warp_max_abs(float v) {
 // maximum is shared (equal |values|, or an all-zero remaining column, where retired lanes "hit" as well)
 // retires several lanes at once, the survivors then do not add up to one and the matrix is redone
 // by the exact search -- the same rule as the integer form.
+// `img` is the tile image, `row0` the tile row of the first of the MI matrices searched in lock step.
 template <typename T, int N, int MODE, int MI>
-__device__ __forceinline__ void prepass_rowwise_swz(const unsigned char* img0, int* perm0, const int8_t* slot_rank, int lane) {
+__device__ __forceinline__ void prepass_rowwise_swz(const unsigned char* img, int row0, int* perm0, const int8_t* slot_rank, int lane) {
     using U = typename FpBits<T>::U;
-    constexpr int ES = sizeof(T), EPV = 16 / ES, RB = N * ES, MAT = N * RB;
+    constexpr int ES = sizeof(T), EPV = 16 / ES, RB = (N * ES + 127) / 128 * 128;
     const int row = (lane < N) ? lane : 0;
     T x[MI][EPV];
     if constexpr (sizeof(T) == 4 && (LUB_PREPASS_F32 != 0)) {
@@ -188,7 +194,7 @@ __device__ __forceinline__ void prepass_rowwise_swz(const unsigned char* img0, i
             if ((k % EPV) == 0) {
 #pragma unroll
                 for (int m = 0; m < MI; ++m)
-                    ld_vec<T, EPV>(reinterpret_cast<const T*>(img0 + m * MAT + swz_byte<RB>(row, (k / EPV) << 4)), x[m]);
+                    ld_vec<T, EPV>(reinterpret_cast<const T*>(img + swz_byte<RB>(row0 + m * N + row, (k / EPV) << 4)), x[m]);
             }
             float v[MI], mx[MI];
 #pragma unroll
@@ -208,7 +214,7 @@ __device__ __forceinline__ void prepass_rowwise_swz(const unsigned char* img0, i
             if (ok) {
                 if (lane < N) perm0[m * N + ((alive[m] != 0.0f) ? (N - 1) : (int)when[m])] = lane;
             } else {
-                prepass_exact_swz<T, N, MODE>(img0 + m * MAT, perm0 + m * N, slot_rank, lane);
+                prepass_exact_swz<T, N, MODE>(img, row0 + m * N, perm0 + m * N, slot_rank, lane);
             }
         }
     } else {
@@ -221,7 +227,7 @@ __device__ __forceinline__ void prepass_rowwise_swz(const unsigned char* img0, i
             if ((k % EPV) == 0) {
 #pragma unroll
                 for (int m = 0; m < MI; ++m)
-                    ld_vec<T, EPV>(reinterpret_cast<const T*>(img0 + m * MAT + swz_byte<RB>(row, (k / EPV) << 4)), x[m]);
+                    ld_vec<T, EPV>(reinterpret_cast<const T*>(img + swz_byte<RB>(row0 + m * N + row, (k / EPV) << 4)), x[m]);
             }
             U key[MI], mx[MI];
 #pragma unroll
@@ -241,9 +247,57 @@ __device__ __forceinline__ void prepass_rowwise_swz(const unsigned char* img0, i
             if (ok) {
                 if (lane < N) perm0[m * N + when[m]] = lane;
             } else {
-                prepass_exact_swz<T, N, MODE>(img0 + m * MAT, perm0 + m * N, slot_rank, lane);
+                prepass_exact_swz<T, N, MODE>(img, row0 + m * N, perm0 + m * N, slot_rank, lane);
             }
         }
+    }
+}
+
+// Position-wise pivot search (lane = row POSITION) on the swizzled image, for parallel pivoting with N not a
+// power of two: the reference tree (parallel_pivot/luBatchedInplace.cuh:34-42) then never merges some
+// slots into slot 0, and which rows are candidates at step k depends on where they sit.  Same search as
+// the position-wise branch of prepass_warp_ptrs (lub_fast.cuh); only the image addressing differs.
+template <typename T, int N, int MODE, int MI>
+__device__ __forceinline__ void prepass_poswise_swz(const unsigned char* img, int row0, int* perm0, const int8_t* slot_rank, int lane) {
+    using U = typename FpBits<T>::U;
+    constexpr int ES = sizeof(T), RB = (N * ES + 127) / 128 * 128;
+    constexpr unsigned ALL = (N >= 32) ? 0xffffffffu : ((1u << N) - 1u);
+    constexpr unsigned REACH = ReachMask<N>::value;
+    int prow[MI];  // original row sitting at position `lane`
+    unsigned multi[MI];
+#pragma unroll
+    for (int m = 0; m < MI; ++m) { prow[m] = (lane < N) ? lane : 0; multi[m] = 0u; }
+#pragma unroll
+    for (int k = 0; k < N - 1; ++k) {
+        const unsigned vmask = ((MODE == kModeParallel) ? ((REACH << (k + 1)) | (1u << k)) : (ALL << k)) & ALL;
+        const bool valid = (vmask == ((ALL << k) & ALL)) ? (lane >= k && lane < N) : (((vmask >> lane) & 1u) != 0u);
+        U v[MI], mx[MI];
+        unsigned bal[MI];
+#pragma unroll
+        for (int m = 0; m < MI; ++m)
+            v[m] = FpBits<T>::absbits(*reinterpret_cast<const T*>(img + swz_off<RB, ES>(row0 + m * N + prow[m], k)));
+#pragma unroll
+        for (int m = 0; m < MI; ++m) mx[m] = warp_max_bits(valid ? v[m] : U(0));
+#pragma unroll
+        for (int m = 0; m < MI; ++m) bal[m] = __ballot_sync(0xffffffffu, valid && v[m] == mx[m]);
+#pragma unroll
+        for (int m = 0; m < MI; ++m) {
+            const int wl = __ffs(bal[m]) - 1;  // lowest position among the maxima; ties are redone exactly below
+            if (MODE == kModeParallel) multi[m] |= bal[m] & (bal[m] - 1u);
+            const int other = __shfl_sync(0xffffffffu, prow[m], lane == k ? wl : k);
+            prow[m] = (lane == k || lane == wl) ? other : prow[m];
+        }
+    }
+#pragma unroll
+    for (int m = 0; m < MI; ++m)
+        if (lane < N) perm0[m * N + lane] = prow[m];
+    if (MODE == kModeParallel) {
+#pragma unroll
+        for (int m = 0; m < MI; ++m)
+            if (multi[m] != 0u) {  // warp-uniform, rare (needs two equal |values| in one column)
+                __syncwarp();
+                prepass_exact_swz<T, N, MODE>(img, row0 + m * N, perm0 + m * N, slot_rank, lane);
+            }
     }
 }
 
@@ -263,7 +317,7 @@ lub_tma_kernel(const __grid_constant__ CUtensorMap tmap, T* __restrict__ A, int3
     constexpr bool VIA_IMG = (MODE != kModeNone) || OUTIMG;  // results go through the image and a bulk store
     using L = TmaLayout<T, N, GR, GC, MODE>;
     constexpr int G = L::G, MPW = L::MPW, LR = L::LR, LC = L::LC, CH = L::CH, CPL = L::CPL;
-    constexpr int RB = L::RB, ES = L::ES, MAT = L::MAT_BYTES;
+    constexpr int RB = L::RB, ES = L::ES;
     extern __shared__ unsigned char smem_dyn[];
 
     const int lane = threadIdx.x & 31;
@@ -316,13 +370,17 @@ lub_tma_kernel(const __grid_constant__ CUtensorMap tmap, T* __restrict__ A, int3
         mbar_wait(bar, parity);
         parity ^= 1u;
 
-        unsigned char* mimg = img + ml * MAT;
+        const int trow0 = ml * N;  // first tile row of this lane's matrix
         int* perm = perm_all + ml * N;
         if (MODE != kModeNone) {
             constexpr int MI = (MPW < 2) ? MPW : 2;
 #pragma unroll 1
-            for (int m = 0; m < MPW; m += MI)
-                prepass_rowwise_swz<T, N, MODE, MI>(img + m * MAT, perm_all + m * N, slot_rank, lane);
+            for (int m = 0; m < MPW; m += MI) {
+                if constexpr (RowwiseOk<N, MODE>::value)
+                    prepass_rowwise_swz<T, N, MODE, MI>(img, m * N, perm_all + m * N, slot_rank, lane);
+                else
+                    prepass_poswise_swz<T, N, MODE, MI>(img, m * N, perm_all + m * N, slot_rank, lane);
+            }
             __syncwarp();
         }
 
@@ -336,8 +394,8 @@ lub_tma_kernel(const __grid_constant__ CUtensorMap tmap, T* __restrict__ A, int3
             if (MODE != kModeNone) prow = rok ? perm[i] : 0;
 #pragma unroll
             for (int q = 0; q < CPL; ++q) {
-                if (rok) {
-                    ld_vec<T, CH>(reinterpret_cast<const T*>(mimg + swz_byte<RB>(prow, (gc * CPL + q) << 4)), &a[li][q * CH]);
+                if (rok) {  // chunks past the data of a padded row read the zeros the TMA unit filled in
+                    ld_vec<T, CH>(reinterpret_cast<const T*>(img + swz_byte<RB>(trow0 + prow, (gc * CPL + q) << 4)), &a[li][q * CH]);
                 } else {
 #pragma unroll
                     for (int w = 0; w < CH; ++w) a[li][q * CH + w] = T(0);
@@ -373,7 +431,7 @@ lub_tma_kernel(const __grid_constant__ CUtensorMap tmap, T* __restrict__ A, int3
                 const bool rok = (li * GR + GR - 1 < N) || (i < N);
 #pragma unroll
                 for (int q = 0; q < CPL; ++q)
-                    if (rok) st_vec<T, CH>(reinterpret_cast<T*>(mimg + swz_byte<RB>(i, (gc * CPL + q) << 4)), &a[li][q * CH]);
+                    if (rok) st_vec<T, CH>(reinterpret_cast<T*>(img + swz_byte<RB>(trow0 + i, (gc * CPL + q) << 4)), &a[li][q * CH]);
             }
             fence_proxy_async();
             __syncwarp();
@@ -389,12 +447,15 @@ lub_tma_kernel(const __grid_constant__ CUtensorMap tmap, T* __restrict__ A, int3
                 const bool rok = (ml < nm) && ((li * GR + GR - 1 < N) || (i < N));
 #pragma unroll
                 for (int q = 0; q < CPL; ++q)
-                    if (rok) st_vec<T, CH>(gm + i * N + q * CH, &a[li][q * CH]);
+                    if (rok && ((GC * CPL <= L::CPR) || (gc * CPL + q < L::CPR))) st_vec<T, CH>(gm + i * N + q * CH, &a[li][q * CH]);
             }
         } else {
             int pcb[LC];  // byte offset of the destination column inside a row
 #pragma unroll
-            for (int lj = 0; lj < LC; ++lj) pcb[lj] = perm[gc * LC + lj] * ES;
+            for (int lj = 0; lj < LC; ++lj) {
+                const int j = gc * LC + lj;
+                pcb[lj] = ((GC * LC <= N) || (j < N)) ? perm[j] * ES : -1;  // padding columns are not written
+            }
             __syncwarp();  // all lanes hold their blocks and columns: the image may be overwritten
 #pragma unroll
             for (int li = 0; li < LR; ++li) {
@@ -402,7 +463,7 @@ lub_tma_kernel(const __grid_constant__ CUtensorMap tmap, T* __restrict__ A, int3
                 const bool rok = (li * GR + GR - 1 < N) || (i < N);
 #pragma unroll
                 for (int lj = 0; lj < LC; ++lj)
-                    if (rok) *reinterpret_cast<T*>(mimg + swz_byte<RB>(i, pcb[lj])) = a[li][lj];
+                    if (rok && ((GC * LC <= N) || (pcb[lj] >= 0))) *reinterpret_cast<T*>(img + swz_byte<RB>(trow0 + i, pcb[lj])) = a[li][lj];
             }
             fence_proxy_async();  // generic-proxy writes -> visible to the TMA unit
             __syncwarp();
@@ -447,10 +508,10 @@ inline cudaError_t make_batch_tmap(CUtensorMap* map, void* A, int n, long long b
     const cuuint32_t estr[4] = {1, 1, 1, 1};
     const int row_bytes = n * (int)sizeof(T);
     CUresult r;
-    if (row_bytes == 128) {  // [batch][n][n], one swizzle line per row
+    if (row_bytes <= 128) {  // [batch][n][n], one swizzle line per row; a shorter row is zero-filled up to the line
         const cuuint64_t dims[3] = {(cuuint64_t)n, (cuuint64_t)n, (cuuint64_t)batch};
         const cuuint64_t strides[2] = {(cuuint64_t)row_bytes, (cuuint64_t)n * row_bytes};
-        const cuuint32_t box[3] = {(cuuint32_t)n, (cuuint32_t)n, (cuuint32_t)mpw};
+        const cuuint32_t box[3] = {(cuuint32_t)(128 / sizeof(T)), (cuuint32_t)n, (cuuint32_t)mpw};
         r = enc(map, dt, 3, A, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                 CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     } else {  // rows of several lines: [batch][n][lines][128 bytes]; the box is still whole matrices, rows contiguous
