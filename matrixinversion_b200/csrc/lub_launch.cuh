@@ -85,6 +85,17 @@ constexpr Cfg pick_v3_cfg(int n, int es, bool pivoting) {
     return Cfg{4, 8};
 }
 
+// Small fp32 matrices need few registers per lane and their tiles are latency-bound (staging wait, pivot
+// search): more resident warps win 10-20 % there (profiles/r01_tune_late.jsonl, "minb" sweep).  From N = 13
+// on the register cap of three blocks per SM spills.
+constexpr int pick_minb(int n, int es, bool pivoting) {
+    if (es != 4) return 2;
+    if (n <= 6) return 4;
+    if (n == 7 || (n >= 9 && n <= 11)) return 3;
+    if (n == 12 && pivoting) return 3;
+    return 2;
+}
+
 template <typename T, int N, int MODE>
 struct V3Cfg {
 #if defined(LUB_FORCE_GR) && defined(LUB_FORCE_GC)
@@ -93,7 +104,8 @@ struct V3Cfg {
     static constexpr Cfg c = pick_v3_cfg(N, (int)sizeof(T), MODE != kModeNone);
     static constexpr int GR = c.gr, GC = c.gc;
 #endif
-    static constexpr int MINB = 2;  // 128 registers per thread, two 256-thread blocks per SM
+    // resident 256-thread blocks per SM the kernel is compiled for (register cap 128 / 80 / 64 per thread)
+    static constexpr int MINB = pick_minb(N, (int)sizeof(T), MODE != kModeNone);
 };
 
 #ifndef LUB_USE_TMA

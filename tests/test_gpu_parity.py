@@ -186,6 +186,27 @@ def test_edge_cases():
         lub.lu_batched_inplace(torch.zeros((2, 4, 4)))  # CPU tensor
 
 
+def test_tma_paths_ragged_batches_leave_neighbours_alone():
+    """The TMA-staged configurations (128-byte rows, 256-byte rows, rows zero-padded to a line) on batch
+    sizes that end inside a warp tile: the bulk tensor store must clip at the batch end, the matrices
+    after it (a guard region in the same allocation) stay untouched, results equal the full-tile path."""
+    guard = 7
+    for n, dtype in ((32, np.float32), (16, np.float64), (32, np.float64), (20, np.float32), (24, np.float32), (28, np.float32)):
+        for mode in MODES:
+            A = synthetic(n, 64 + guard, dtype, dominant=(mode == 0))
+            Xfull, pfull = gpu_invert(A, mode)
+            for B in (1, 2, 3, 5, 9, 64):
+                base = torch.from_numpy(A[: B + guard].copy()).cuda()
+                piv = torch.full((B + guard, n), -1, dtype=torch.int32, device="cuda")
+                lub.lu_batched_inplace(base[:B], piv[:B], mode)
+                torch.cuda.synchronize()
+                got = base.cpu().numpy()
+                assert np.array_equal(got[:B], Xfull[:B], equal_nan=True), (n, dtype, mode, B)
+                assert np.array_equal(got[B:], A[B : B + guard]), ("guard overwritten", n, dtype, mode, B)
+                gp = piv.cpu().numpy()
+                assert np.array_equal(gp[:B], pfull[:B]) and np.all(gp[B:] == -1), (n, dtype, mode, B)
+
+
 def test_numthreads_knob_and_host_pipeline_are_bitwise_equivalent():
     for n, dtype in ((6, np.float32), (18, np.float32), (32, np.float32), (12, np.float64), (32, np.float64)):
         A = synthetic(n, 1001, dtype)
