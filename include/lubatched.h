@@ -67,6 +67,18 @@ int lu_batched_inplace(void* ptr, int32_t* piv, int n, int64_t batch, int pivot_
 int lu_batched_inplace_stream(void* ptr, int32_t* piv, int n, int64_t batch, int pivot_mode, int dtype,
                               void* stream);
 
+/* LU factors only: stops where the reference's k-loop ends
+ * (parallel_pivot/luBatchedInplace.cuh:156-186, serial_pivot/...cuh:130-160,
+ * templated/...cuh:100-110), i.e. before comp_inv / inversion -- the state upstream can only
+ * look at by commenting the inversion out, and the one its disabled checks verifyLU
+ * (templated/verify.hpp:105-186) and verifyLUwithPivoting (parallel_pivot/verify.hpp:157-242)
+ * are written for.  In place: unit-lower L strictly below the diagonal, U on and above it,
+ * rows in pivoted order (output row i factorises input row piv[i]); piv as above.  Values
+ * equal the reference's left-looking Doolittle factors up to rounding.  Not a tuned path. */
+int lu_batched_factor_inplace(void* ptr, int32_t* piv, int n, int64_t batch, int pivot_mode, int dtype);
+int lu_batched_factor_inplace_stream(void* ptr, int32_t* piv, int n, int64_t batch, int pivot_mode, int dtype,
+                                     void* stream);
+
 /* Stream used by lu_batched_inplace and the helpers below on the calling thread
  * (the reference compiles with --default-stream per-thread, templated/run.py:48). */
 int lu_batched_set_stream(void* stream);
@@ -109,6 +121,15 @@ float lu_batched_last_kernel_ms(void);
  * every |r - delta_ij| < thr (the reference hard-codes thr = 1e-3).  Outputs may be NULL. */
 int lu_batched_verify_inv(const void* A, const void* Ainv, int n, int64_t batch, int dtype, double thr,
                           int64_t* n_correct, int64_t* n_incorrect, double* max_abs_dev);
+
+/* verifyLU (templated/verify.hpp:105-186) and verifyLUwithPivoting
+ * (parallel_pivot/verify.hpp:157-242) on HOST buffers: L = unit-lower part of LU, U = its upper
+ * part; a factorisation is correct iff every |(P A)(i,j) - sum_l L(i,l) U(l,j)| < thr (sum in T).
+ * piv = the permutation vectors written by lu_batched_factor_inplace (row i of P A is row piv[i]
+ * of A), or NULL for no pivoting (= verifyLU).  The reference permutes one template with pivotedA
+ * because all its matrices are equal; here every matrix has its own vector. */
+int lu_batched_verify_lu(const void* A, const void* LU, const int32_t* piv, int n, int64_t batch, int dtype,
+                         double thr, int64_t* n_correct, int64_t* n_incorrect, double* max_abs_dev);
 
 /* Same predicate evaluated on the DEVICE (buffers are device pointers); used by the sweep
  * driver so that a 1M-matrix check does not need two 4 GB host copies

@@ -48,6 +48,8 @@ _FP = ctypes.POINTER(ctypes.c_float)
 SIGNATURES = {
     "lu_batched_inplace": (ctypes.c_int, [_P, _P, ctypes.c_int, ctypes.c_int64, ctypes.c_int, ctypes.c_int]),
     "lu_batched_inplace_stream": (ctypes.c_int, [_P, _P, ctypes.c_int, ctypes.c_int64, ctypes.c_int, ctypes.c_int, _P]),
+    "lu_batched_factor_inplace": (ctypes.c_int, [_P, _P, ctypes.c_int, ctypes.c_int64, ctypes.c_int, ctypes.c_int]),
+    "lu_batched_factor_inplace_stream": (ctypes.c_int, [_P, _P, ctypes.c_int, ctypes.c_int64, ctypes.c_int, ctypes.c_int, _P]),
     "lu_batched_set_stream": (ctypes.c_int, [_P]),
     "lu_batched_inplace_host": (ctypes.c_int, [_P, _P, ctypes.c_int, ctypes.c_int64, ctypes.c_int, ctypes.c_int]),
     "lu_batched_set_threads": (ctypes.c_int, [ctypes.c_int]),
@@ -57,6 +59,7 @@ SIGNATURES = {
     "lu_batched_enable_timing": (ctypes.c_int, [ctypes.c_int]),
     "lu_batched_last_kernel_ms": (ctypes.c_float, []),
     "lu_batched_verify_inv": (ctypes.c_int, [_P, _P, ctypes.c_int, ctypes.c_int64, ctypes.c_int, ctypes.c_double, _I64P, _I64P, _DP]),
+    "lu_batched_verify_lu": (ctypes.c_int, [_P, _P, _P, ctypes.c_int, ctypes.c_int64, ctypes.c_int, ctypes.c_double, _I64P, _I64P, _DP]),
     "lu_batched_verify_inv_device": (ctypes.c_int, [_P, _P, ctypes.c_int, ctypes.c_int64, ctypes.c_int, ctypes.c_double, _I64P, _I64P, _DP]),
     "lu_batched_read_tokens": (ctypes.c_int, [ctypes.c_char_p, _P, ctypes.c_int64, ctypes.c_int]),
     "lu_batched_replicate": (ctypes.c_int, [_P, _P, ctypes.c_int, ctypes.c_int64, ctypes.c_int]),

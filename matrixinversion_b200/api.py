@@ -112,6 +112,50 @@ def lu_batched_inplace(A, piv=None, pivot_mode="parallel", stream=None):
     return A
 
 
+def lu_batched_factor_inplace(A, piv=None, pivot_mode="parallel", stream=None):
+    """LU factors only, in place: the state of the reference's shared-memory matrix
+    after its k-loop (parallel_pivot/luBatchedInplace.cuh:156-186), which upstream's disabled
+    `verifyLU` / `verifyLUwithPivoting` are written for.  A: contiguous CUDA torch tensor
+    [batch, n, n]; piv: optional CUDA int32 [batch, n].  Unit-lower L below the diagonal, U on and
+    above it, rows in pivoted order.  Returns A."""
+    import torch
+    L = _lib.lib()
+    mode = _mode(pivot_mode)
+    batch, n = _check_batch(A.shape)
+    if not (_is_torch(A) and A.is_cuda and A.is_contiguous()):
+        raise LubError(-4, "A must be a contiguous CUDA torch tensor")
+    pptr = None
+    if piv is not None:
+        if not (piv.is_cuda and piv.is_contiguous() and piv.dtype == torch.int32 and tuple(piv.shape) == (batch, n)):
+            raise LubError(-4, "piv must be a contiguous CUDA int32 [batch, n] tensor")
+        pptr = piv.data_ptr()
+    with torch.cuda.device(A.device):
+        s = stream if stream is not None else torch.cuda.current_stream(A.device)
+        sp = s.cuda_stream if hasattr(s, "cuda_stream") else int(s)
+        check(L.lu_batched_factor_inplace_stream(A.data_ptr(), pptr, n, batch, mode, _dtype_code(A.dtype), sp))
+    return A
+
+
+def verify_lu(A, LU, piv=None, thr: float = 1e-3):
+    """verifyLU (templated/verify.hpp:105-186) / verifyLUwithPivoting (parallel_pivot/verify.hpp:157-242)
+    on host arrays: returns (correct, incorrect, max |PA - L U|).  piv: int32 [batch, n] permutation
+    vectors (None = no pivoting)."""
+    L = _lib.lib()
+    A = np.ascontiguousarray(A)
+    LU = np.ascontiguousarray(LU, dtype=A.dtype)
+    batch, n = _check_batch(A.shape)
+    pptr = None
+    if piv is not None:
+        piv = np.ascontiguousarray(piv, dtype=np.int32)
+        if piv.shape != (batch, n):
+            raise LubError(-4, "piv must be int32 [batch, n]")
+        pptr = piv.ctypes.data
+    ok, bad, dev = ctypes.c_int64(), ctypes.c_int64(), ctypes.c_double()
+    check(L.lu_batched_verify_lu(A.ctypes.data, LU.ctypes.data, pptr, n, batch, _dtype_code(A.dtype), thr,
+                                 ctypes.byref(ok), ctypes.byref(bad), ctypes.byref(dev)))
+    return ok.value, bad.value, dev.value
+
+
 def lu_batched_inplace_ptr(ptr: int, piv_ptr, n: int, batch: int, pivot_mode, dtype, stream_ptr: int = 0) -> None:
     """Raw-pointer form: exactly the C ABI call (device pointers as integers)."""
     check(_lib.lib().lu_batched_inplace_stream(ptr, piv_ptr, n, batch, _mode(pivot_mode), _dtype_code(dtype), stream_ptr))

@@ -217,7 +217,13 @@ __device__ __forceinline__ void row_update(double (&a)[LC], const double (&r)[LC
 
 // ---- the kernel ---------------------------------------------------------------------------
 
-template <typename T, int N, int GR, int GC, int MODE>
+// LUONLY: stop after the factorisation and write the factors instead of the inverse -- the state the
+// reference's shared-memory matrix is in after its k-loop (parallel_pivot/luBatchedInplace.cuh:156-186,
+// before comp_inv): unit-lower L strictly below the diagonal, U on and above it, rows in pivoted order
+// (row i of the output factorises input row piv[i]).  This is what verifyLU / verifyLUwithPivoting
+// (templated/verify.hpp:105-186, parallel_pivot/verify.hpp:157-242) check.  Right-looking elimination
+// on the same lane grid; same values as the reference's left-looking Doolittle up to rounding.
+template <typename T, int N, int GR, int GC, int MODE, bool LUONLY = false>
 __global__ void __launch_bounds__(kMaxThreads)
 lub_invert_kernel(T* __restrict__ A, int32_t* __restrict__ piv, long long batch) {
     using L = Layout<T, N, GR, GC, MODE>;
@@ -275,6 +281,44 @@ lub_invert_kernel(T* __restrict__ A, int32_t* __restrict__ piv, long long batch)
             }
         }
 
+        if constexpr (LUONLY) {
+            // ---- right-looking LU: row k is final at step k, column k below it takes the multipliers
+#pragma unroll
+            for (int k = 0; k < N - 1; ++k) {
+                const int gro = k % GR, lk = k / GR;
+                const int gco = k % GC, ck = k / GC;
+                const bool own_col = (GC == 1) || (gc == gco);
+                T r[LC], c[LR];
+#pragma unroll
+                for (int lj = 0; lj < LC; ++lj)
+                    r[lj] = (GR > 1) ? shfl_t(a[lk][lj], grp_base + gro * GC + gc) : a[lk][lj];
+#pragma unroll
+                for (int li = 0; li < LR; ++li)
+                    c[li] = (GC > 1) ? shfl_t(a[li][ck], grp_base + gr * GC + gco) : a[li][ck];
+                const T pv = (GC > 1) ? shfl_t(r[ck], grp_base + gr * GC + gco) : r[ck];
+                const T rinv = rcp_t(pv);
+#pragma unroll
+                for (int lj = 0; lj < LC; ++lj) r[lj] = (lj * GC + gc > k) ? r[lj] : T(0);  // only columns right of k change
+#pragma unroll
+                for (int li = 0; li < LR; ++li) {
+                    const T l = (li * GR + gr > k) ? c[li] * rinv : T(0);                   // only rows below k change
+                    row_update<LC>(a[li], r, -l);
+                    a[li][ck] = (own_col && (li * GR + gr > k)) ? l : a[li][ck];
+                }
+            }
+            __syncwarp();  // all lanes finished reading the image
+#pragma unroll
+            for (int li = 0; li < LR; ++li) {
+                const int i = li * GR + gr;
+                const bool rok = (li * GR + GR - 1 < N) || (i < N);
+#pragma unroll
+                for (int lj = 0; lj < LC; ++lj) {
+                    const int j = lj * GC + gc;
+                    const bool ok = rok && ((lj * GC + GC - 1 < N) || (j < N));
+                    if (ok) mimg[i * N + j] = a[li][lj];
+                }
+            }
+        } else {
         // ---- Gauss-Jordan, deferred scaling ----------------------------------------------
         T dinv[LR];
 #pragma unroll
@@ -327,6 +371,7 @@ lub_invert_kernel(T* __restrict__ A, int32_t* __restrict__ piv, long long batch)
                 const bool ok = rok && ((lj * GC + GC - 1 < N) || (j < N));
                 if (ok) mimg[i * N + pcol[lj]] = a[li][lj] * dinv[li];
             }
+        }
         }
         __syncwarp();
         copy_out<T>(gspan, img, total, lane);

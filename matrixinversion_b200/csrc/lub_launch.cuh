@@ -24,7 +24,9 @@ struct LaunchInfo {
     const char* kernel;
 };
 
-// int launcher(A, piv, batch, threads (0 = default), stream, info (may be NULL), dry_run)
+// int launcher(A, piv, batch, threads (0 = default), stream, info (may be NULL), flags)
+// flags: bit 0 = dry run (fill `info`, launch nothing), bit 1 = LU factors only (no inversion)
+constexpr int kLaunchDryRun = 1, kLaunchLuOnly = 2;
 using LaunchFn = cudaError_t (*)(void*, int32_t*, long long, int, cudaStream_t, LaunchInfo*, int);
 
 // Lane layout choice.  A matrix is spread over G = GR x GC lanes, each holding an LR x LC
@@ -166,13 +168,36 @@ cudaError_t prepare(K kern, KernelCache& c, int dev, int threads, int smem) {
 
 template <typename T, int N, int MODE>
 cudaError_t launch(void* A, int32_t* piv, long long batch, int threads, cudaStream_t stream,
-                   LaunchInfo* info, int dry_run) {
+                   LaunchInfo* info, int flags) {
+    const int dry_run = flags & kLaunchDryRun;
     if (threads <= 0) threads = 256;
     const int warps = threads / 32;
     int dev = 0;
     cudaError_t err = cudaGetDevice(&dev);
     if (err != cudaSuccess) return err;
     if (dev < 0 || dev >= kMaxDevices) return cudaErrorInvalidDevice;
+
+    if (flags & kLaunchLuOnly) {  // factors only: the generic kernel's LU variant (not a tuned path)
+        using AC = AutoCfg<T, N, MODE>;
+        using GLU = Layout<T, N, AC::GR, AC::GC, MODE>;
+        static KernelCache cache_lu[kMaxDevices] = {};
+        auto kern = lub_invert_kernel<T, N, AC::GR, AC::GC, MODE, true>;
+        const int smem_lu = GLU::HEADER_BYTES + warps * GLU::WARP_BYTES;
+        KernelCache& cl = cache_lu[dev];
+        err = prepare(kern, cl, dev, threads, smem_lu);
+        if (err != cudaSuccess) return err;
+        const long long ntiles_lu = (batch + GLU::MPW - 1) / GLU::MPW;
+        long long blocks_lu = (ntiles_lu + warps - 1) / warps;
+        if (blocks_lu > (long long)cl.sms * cl.blocks_per_sm) blocks_lu = (long long)cl.sms * cl.blocks_per_sm;
+        if (info) {
+            info->threads_per_block = threads; info->threads_per_matrix = GLU::G; info->matrices_per_block = warps * GLU::MPW;
+            info->num_blocks = blocks_lu; info->dyn_smem_bytes = smem_lu; info->regs_per_thread = cl.regs;
+            info->blocks_per_sm = cl.blocks_per_sm; info->kernel = "lub_invert_kernel<LUONLY>";
+        }
+        if (dry_run || batch == 0) return cudaSuccess;
+        kern<<<(unsigned)blocks_lu, threads, smem_lu, stream>>>(static_cast<T*>(A), piv, batch);
+        return cudaGetLastError();
+    }
 
     using VC = V3Cfg<T, N, MODE>;
     // fp64 with a multi-lane layout runs the rolled-step kernel (lub_v4.cuh): 5-18 % faster there

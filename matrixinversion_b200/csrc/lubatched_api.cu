@@ -65,8 +65,10 @@ int check_args(int n, int64_t batch, int mode, int dtype) {
 
 size_t esize(int dtype) { return dtype == LUB_DTYPE_F32 ? 4 : 8; }
 
+// flags: lub::kLaunchDryRun | lub::kLaunchLuOnly
 int launch_on(void* ptr, int32_t* piv, int n, int64_t batch, int mode, int dtype, cudaStream_t s,
-              lub::LaunchInfo* info, int dry) {
+              lub::LaunchInfo* info, int flags) {
+    const bool dry = (flags & lub::kLaunchDryRun) != 0;
     int rc = check_args(n, batch, mode, dtype);
     if (rc != LUB_OK) return rc;
     if (!dry && batch > 0) {
@@ -80,7 +82,7 @@ int launch_on(void* ptr, int32_t* piv, int n, int64_t batch, int mode, int dtype
         if (!g_ev0) { CU(cudaEventCreate(&g_ev0)); CU(cudaEventCreate(&g_ev1)); }
         CU(cudaEventRecord(g_ev0, s));
     }
-    cudaError_t e = fn(ptr, piv, (long long)batch, g_threads, s, info, dry);
+    cudaError_t e = fn(ptr, piv, (long long)batch, g_threads, s, info, flags);
     if (e != cudaSuccess) return cuda_fail(e, "kernel launch");
     if (timed) { CU(cudaEventRecord(g_ev1, s)); g_ev_valid = true; }
     return LUB_OK;
@@ -109,6 +111,45 @@ void verify_host(const T* A, const T* X, int n, int64_t batch, double thr, int64
                 else if ((double)d > worst) worst = (double)d;
             }
         if (id_cnt == n && off_cnt == n * (n - 1)) good++;
+    }
+    if (ok) *ok = good;
+    if (bad) *bad = batch - good;
+    if (dev) *dev = saw_nan ? NAN : worst;
+}
+
+// verifyLU (templated/verify.hpp:105-186) / verifyLUwithPivoting (parallel_pivot/verify.hpp:157-242):
+// L = unit-lower part of LU, U = upper part, every |(P A)(i,j) - sum_l L(i,l) U(l,j)| < thr, the sum
+// accumulated in T over ALL l (zeros included, as the reference does).  The reference builds P A once
+// from pivotedA because all its matrices are equal; here each matrix brings its own permutation vector.
+template <typename T>
+void verify_lu_host(const T* A, const T* LU, const int32_t* piv, int n, int64_t batch, double thr, int64_t* ok, int64_t* bad, double* dev) {
+    const T threshold = static_cast<T>(thr);
+    int64_t good = 0;
+    double worst = 0.0;
+    bool saw_nan = false;
+#pragma omp parallel for schedule(static) reduction(+ : good) reduction(max : worst) reduction(|| : saw_nan)
+    for (int64_t k = 0; k < batch; ++k) {
+        const T* a = A + k * (int64_t)n * n;
+        const T* lu = LU + k * (int64_t)n * n;
+        const int32_t* p = piv ? piv + k * (int64_t)n : nullptr;
+        int cnt = 0;
+        for (int i = 0; i < n; ++i) {
+            const int src = p ? p[i] : i;
+            for (int j = 0; j < n; ++j) {
+                T r = T(0);
+                for (int l = 0; l < n; ++l) {
+                    const T lv = (l < i) ? lu[i * n + l] : (l == i ? T(1) : T(0));
+                    const T uv = (l <= j) ? lu[l * n + j] : T(0);
+                    r += lv * uv;
+                }
+                const T ref = (src >= 0 && src < n) ? a[src * n + j] : T(NAN);
+                const T d = std::fabs(ref - r);
+                if (d < threshold) cnt++;
+                if (d != d) saw_nan = true;
+                else if ((double)d > worst) worst = (double)d;
+            }
+        }
+        if (cnt == n * n) good++;
     }
     if (ok) *ok = good;
     if (bad) *bad = batch - good;
@@ -213,6 +254,24 @@ int lu_batched_inplace_stream(void* ptr, int32_t* piv, int n, int64_t batch, int
 
 int lu_batched_inplace(void* ptr, int32_t* piv, int n, int64_t batch, int pivot_mode, int dtype) {
     return launch_on(ptr, piv, n, batch, pivot_mode, dtype, g_stream, nullptr, 0);
+}
+
+int lu_batched_factor_inplace_stream(void* ptr, int32_t* piv, int n, int64_t batch, int pivot_mode, int dtype, void* stream) {
+    return launch_on(ptr, piv, n, batch, pivot_mode, dtype, static_cast<cudaStream_t>(stream), nullptr, lub::kLaunchLuOnly);
+}
+
+int lu_batched_factor_inplace(void* ptr, int32_t* piv, int n, int64_t batch, int pivot_mode, int dtype) {
+    return launch_on(ptr, piv, n, batch, pivot_mode, dtype, g_stream, nullptr, lub::kLaunchLuOnly);
+}
+
+int lu_batched_verify_lu(const void* A, const void* LU, const int32_t* piv, int n, int64_t batch, int dtype, double thr,
+                         int64_t* n_correct, int64_t* n_incorrect, double* max_abs_dev) {
+    if (n < 1 || n > 1024) return fail(LUB_ERR_BAD_N, "n out of range");
+    if (batch < 0 || (!A && batch) || (!LU && batch)) return fail(LUB_ERR_BAD_ARG, "bad buffers");
+    if (dtype == LUB_DTYPE_F32) verify_lu_host(static_cast<const float*>(A), static_cast<const float*>(LU), piv, n, batch, thr, n_correct, n_incorrect, max_abs_dev);
+    else if (dtype == LUB_DTYPE_F64) verify_lu_host(static_cast<const double*>(A), static_cast<const double*>(LU), piv, n, batch, thr, n_correct, n_incorrect, max_abs_dev);
+    else return fail(LUB_ERR_BAD_DTYPE, "dtype must be 0 or 1");
+    return LUB_OK;
 }
 
 int lu_batched_geometry(int n, int64_t batch, int pivot_mode, int dtype, int* threads_per_block,

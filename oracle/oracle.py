@@ -180,6 +180,22 @@ def ref_verify_inv(A: np.ndarray, X: np.ndarray):
     return ok.value, bad.value
 
 
+def ref_verify_lu_piv(PA: np.ndarray, LU: np.ndarray):
+    """The reference's own verifyLUwithPivoting (parallel_pivot/verify.hpp:157-242): PA = ONE permuted
+    n x n matrix (what main() would pass after pivotedA), LU = [batch, n, n] factors -> (correct, incorrect)."""
+    PA = np.ascontiguousarray(PA)
+    LU = np.ascontiguousarray(LU, dtype=PA.dtype)
+    b, n, _ = LU.shape
+    ct = _ct(PA.dtype)
+    f = getattr(_ref("ref_verify"), "ref_verify_lu_piv_" + _suf(PA.dtype))
+    f.restype = None
+    f.argtypes = [ctypes.POINTER(ct), ctypes.POINTER(ct), ctypes.c_int, ctypes.c_int,
+                  ctypes.POINTER(ctypes.c_longlong), ctypes.POINTER(ctypes.c_longlong)]
+    ok, bad = ctypes.c_longlong(), ctypes.c_longlong()
+    f(_ptr(PA, ct), _ptr(LU, ct), n, b, ctypes.byref(ok), ctypes.byref(bad))
+    return ok.value, bad.value
+
+
 def ref_calc_cond_num(A: np.ndarray) -> float:
     A = np.ascontiguousarray(A)
     ct = _ct(A.dtype)

@@ -133,6 +133,42 @@ def test_host_verify_inv_equals_oracle_and_golden(inputs, golden):
     assert lub.verify_inv(A, X)[:2] == (38, 2) == O.verify_inv(A, X)[:2]
 
 
+def test_host_verify_lu_equals_reference_verdicts(inputs):
+    """lu_batched_verify_lu = verifyLU / verifyLUwithPivoting (templated/verify.hpp:105-186,
+    parallel_pivot/verify.hpp:157-242): same verdicts as the reference's own function gave (golden file
+    made by tests/golden/make_golden_lu.py through oracle/_ref) on the oracle's factors of the reference's
+    inputs, for an intact factorisation and for one with a single entry off by 0.01; the oracle's factors
+    themselves have not drifted; and, when oracle/_ref is present, the live reference agrees too."""
+    g = np.load(os.path.join(ROOT, "tests", "golden", "golden_verify_lu.npz"))
+    seen = 0
+    for key in g.files:
+        if not key.startswith("ref_verify_lu/"):
+            continue
+        _, name, suf, mode, n = key.split("/")
+        mode, n = int(mode), int(n)
+        dt = np.float32 if suf == "f32" else np.float64
+        A = template(inputs, name, n, dt)
+        with np.errstate(all="ignore"):
+            LU, perm = O.lu_batched(A[None], mode, lu_only=True)
+        if suf == "f32":
+            assert np.array_equal(LU[0], g["orc_lu/%s/%d/%d" % (name, mode, n)]), key
+        bad_lu = LU.copy()
+        bad_lu[0, n - 1, n - 1] += 0.01
+        ours = [*lub.verify_lu(A[None], LU, perm)[:2], *lub.verify_lu(A[None], bad_lu, perm)[:2]]
+        assert ours == g[key].tolist(), (key, ours, g[key].tolist())
+        if O.have_ref("ref_verify") and seen % 7 == 0:
+            assert list(O.ref_verify_lu_piv(A[perm[0]], LU)) == ours[:2], key
+        seen += 1
+    assert seen > 200
+    # no pivoting = verifyLU: piv may be NULL; several distinct matrices, one broken, one NaN
+    A = synthetic(9, 40, np.float64, dominant=True)
+    LU, _ = O.lu_batched(A, 0, lu_only=True)
+    LU[3, 2, 5] += 0.01
+    LU[17, 0, 0] = np.nan
+    assert lub.verify_lu(A, LU)[:2] == (38, 2)
+    assert np.isnan(lub.verify_lu(A, LU)[2])
+
+
 def test_default_num_threads_table():
     """templated/run.py:201-223."""
     table = {1: 32, 2: 32, 3: 30, 4: 32, 5: 30, 6: 30, 7: 28, 8: 32, 9: 27, 10: 30, 11: 22, 12: 24, 13: 26,
