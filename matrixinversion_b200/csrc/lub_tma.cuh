@@ -301,6 +301,15 @@ __device__ __forceinline__ void prepass_poswise_swz(const unsigned char* img, in
     }
 }
 
+// 32-byte global store (STG.256, sm_100): one full sector per lane and instruction
+__device__ __forceinline__ void st_global_256(float* p, const float* v) {
+    asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]),
+                 "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7]) : "memory");
+}
+__device__ __forceinline__ void st_global_256(double* p, const double* v) {
+    asm volatile("st.global.v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(p), "d"(v[0]), "d"(v[1]), "d"(v[2]), "d"(v[3]) : "memory");
+}
+
 // One warp = one tile of MPW matrices; persistent over tiles.  BSYNC as in lub_v3_kernel.
 // PF (no-pivot mode only): the image is free once the registers are loaded, so the next tile is
 // requested right then, in place, and lands while this one is eliminated (+2.5 %).  The same idea
@@ -309,7 +318,10 @@ __device__ __forceinline__ void prepass_poswise_swz(const unsigned char* img, in
 // and the LSU pipe, not by the wait for its input, so that variant is not kept.
 // OUTIMG (no-pivot mode only, excludes PF): the results leave like in the pivot modes -- 16-byte vector
 // stores into the swizzled image, then one bulk tensor store -- instead of straight from the registers.
-template <typename T, int N, int GR, int GC, int MODE, int MINB = 2, bool BSYNC = true, bool PF = false, bool OUTIMG = false>
+// ST256 (register-store path only): 32-byte stores; needs a 32-byte aligned batch and an even number of
+// chunks per lane.
+template <typename T, int N, int GR, int GC, int MODE, int MINB = 2, bool BSYNC = true, bool PF = false, bool OUTIMG = false,
+          bool ST256 = false>
 __global__ void __launch_bounds__(kMaxThreads, MINB)
 lub_tma_kernel(const __grid_constant__ CUtensorMap tmap, T* __restrict__ A, int32_t* __restrict__ piv, long long batch) {
     static_assert(!PF || MODE == kModeNone, "in-place prefetch: the pivot modes need the image for the column scatter");
@@ -445,9 +457,16 @@ lub_tma_kernel(const __grid_constant__ CUtensorMap tmap, T* __restrict__ A, int3
             for (int li = 0; li < LR; ++li) {
                 const int i = li * GR + gr;
                 const bool rok = (ml < nm) && ((li * GR + GR - 1 < N) || (i < N));
+                if constexpr (ST256) {
+                    static_assert(!ST256 || (CPL % 2 == 0 && GC * CPL <= L::CPR), "32-byte stores: whole chunk pairs of real data");
 #pragma unroll
-                for (int q = 0; q < CPL; ++q)
-                    if (rok && ((GC * CPL <= L::CPR) || (gc * CPL + q < L::CPR))) st_vec<T, CH>(gm + i * N + q * CH, &a[li][q * CH]);
+                    for (int q = 0; q < CPL; q += 2)
+                        if (rok) st_global_256(gm + i * N + q * CH, &a[li][q * CH]);
+                } else {
+#pragma unroll
+                    for (int q = 0; q < CPL; ++q)
+                        if (rok && ((GC * CPL <= L::CPR) || (gc * CPL + q < L::CPR))) st_vec<T, CH>(gm + i * N + q * CH, &a[li][q * CH]);
+                }
             }
         } else {
             int pcb[LC];  // byte offset of the destination column inside a row

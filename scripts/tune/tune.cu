@@ -73,7 +73,7 @@ template <typename T, int N, int GR, int GC, int MODE, int MINB, int BS>
 struct VT {
     using L = TmaLayout<T, N, GR, GC, MODE>;
     static constexpr bool PF = (BS & 2) != 0;
-    static constexpr auto kern() { return lub_tma_kernel<T, N, GR, GC, MODE, MINB, (BS & 1) != 0, PF, (BS & 4) != 0>; }
+    static constexpr auto kern() { return lub_tma_kernel<T, N, GR, GC, MODE, MINB, (BS & 1) != 0, PF, (BS & 4) != 0, (BS & 8) != 0>; }
     static void set_attr(int smem) { cudaFuncSetAttribute(kern(), cudaFuncAttributeMaxDynamicSharedMemorySize, smem); }
     static void launch(void* A, int* piv, long long batch, unsigned blocks, int threads, int smem, cudaStream_t s) {
         CUtensorMap map;
