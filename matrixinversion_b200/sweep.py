@@ -21,6 +21,12 @@ What is fixed: the reference's parser `break`s on the "Kernel execution time" li
 printed before "Incorrect inversions", so its sweep never records correctness.
 Here `incorrect_inversions` is the verifyInv-compatible count of every run.
 Extra keys (additive): gbps, matrices_per_s, gflops_2n3, frac_hbm_roofline, cublas_ms (--cublas).
+Several GPUs (BASELINE config 4 "at 1/2/4/8 B200"): launched under
+`python -m torch.distributed.run --nproc-per-node G -m matrixinversion_b200.sweep ...` every rank
+inverts its contiguous slice of each batch (sharding.shard_range: strong scaling, the batch sizes of
+the reference's loop stay what they are), a run's time is the maximum of the ranks' kernel times, the
+incorrect counts are summed (sharding.reduce_verdict: the only collective, two scalars), rank 0 writes
+the files and records `n_gpus`.
 """
 from __future__ import annotations
 
@@ -33,6 +39,7 @@ import shutil
 import numpy as np
 
 from . import _lib, api
+from .sharding import reduce_verdict, shard_range
 
 BATCH_NAMES = {100000: "100k", 500000: "500k", 1000000: "1M"}
 
@@ -73,14 +80,28 @@ def save_results(results, filepath):
         json.dump(results, f, indent=4)
 
 
-def run_config(n, batch, mode, dtype, template, runs, warm=False, cublas=False, peak_gbps=None):
-    """`runs` cold single launches of one configuration; returns the JSON entry."""
+def _max_over_ranks(ms, world):
+    if world == 1:
+        return ms
+    import torch
+    import torch.distributed as dist
+    t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def run_config(n, batch, mode, dtype, template, runs, warm=False, cublas=False, peak_gbps=None, rank=0, world=1):
+    """`runs` cold single launches of one configuration; returns the JSON entry.  With world > 1 this
+    rank works on its slice of the batch; times are maxima over ranks, incorrect counts sums."""
     import torch
 
+    total_batch = batch
+    lo, hi = shard_range(total_batch, rank, world)
+    batch = hi - lo
     tdt = torch.float32 if np.dtype(dtype) == np.float32 else torch.float64
     dT = torch.from_numpy(np.ascontiguousarray(template)).cuda()
-    orig = dT.unsqueeze(0).expand(batch, n, n).contiguous()   # main()'s replicate loop
-    geo = api.geometry(n, batch, mode, dtype)
+    orig = dT.unsqueeze(0).expand(batch, n, n).contiguous()   # main()'s replicate loop (this rank's slice)
+    geo = api.geometry(n, max(batch, 1), mode, dtype)
     runtimes, incorrect, warm_ms = [], [], []
     A = torch.empty_like(orig)
     api.enable_timing(True)
@@ -88,20 +109,23 @@ def run_config(n, batch, mode, dtype, template, runs, warm=False, cublas=False, 
         for r in range(runs):
             A.copy_(orig)
             torch.cuda.synchronize()
+            if world > 1:
+                torch.distributed.barrier()
             api.lu_batched_inplace(A, None, mode)
-            runtimes.append(api.last_kernel_ms())
-            _, bad, _ = api.verify_inv(orig, A)
-            incorrect.append(bad)
+            runtimes.append(_max_over_ranks(api.last_kernel_ms() if batch else 0.0, world))
+            _, bad, dev = api.verify_inv(orig, A) if batch else (0, 0, 0.0)
+            incorrect.append(reduce_verdict(bad, 0.0 if dev != dev else dev)[0] if world > 1 else bad)
         if warm:
             for r in range(runs):
                 A.copy_(orig)
                 api.lu_batched_inplace(A, None, mode)
-                warm_ms.append(api.last_kernel_ms())
+                warm_ms.append(_max_over_ranks(api.last_kernel_ms() if batch else 0.0, world))
     finally:
         api.enable_timing(False)
     es = np.dtype(dtype).itemsize
     best = min(runtimes)
-    extra = {"reference_num_threads": api.default_num_threads(n), "threads_per_matrix": geo.threads_per_matrix,
+    batch = total_batch
+    extra = {"n_gpus": world, "reference_num_threads": api.default_num_threads(n), "threads_per_matrix": geo.threads_per_matrix,
              "matrices_per_block": geo.matrices_per_block, "num_blocks": geo.num_blocks,
              "matrices_per_s": batch / (best * 1e-3), "gbps": 2.0 * n * n * es * batch / (best * 1e-3) / 1e9,
              "gflops_2n3": 2.0 * n ** 3 * batch / (best * 1e-3) / 1e9}
@@ -109,7 +133,7 @@ def run_config(n, batch, mode, dtype, template, runs, warm=False, cublas=False, 
         extra["frac_hbm_roofline"] = extra["gbps"] / peak_gbps
     if warm_ms:
         extra["warm_runtimes"] = warm_ms
-    if cublas:
+    if cublas and world == 1:
         C = _lib.cublas_lib()
         dst = torch.empty_like(orig)
         t1, t2 = ctypes.c_float(), ctypes.c_float()
@@ -140,26 +164,45 @@ def main(argv=None):
     lo, _, hi = a.sizes.partition("-")
     sizes = range(int(lo), int(hi or lo) + 1)
     dtype = np.dtype(a.dtype)
-    base, ncu_dir, runtime_dir = create_output_directories(a.out)
+    rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+    if world > 1:  # one process per GPU (torch.distributed.run); NCCL only for the scalar reductions
+        import torch
+        import torch.distributed as dist
+        local = int(os.environ.get("LOCAL_RANK", "0"))
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    if rank == 0:
+        base, ncu_dir, runtime_dir = create_output_directories(a.out)
+    else:
+        base, ncu_dir, runtime_dir = a.out, os.path.join(a.out, "ncu_profiles"), os.path.join(a.out, "runtime_results")
     results = {}
     try:
         for batch in [int(b) for b in a.batches.split(",")]:
             name = BATCH_NAMES.get(batch, str(batch))
-            os.makedirs(os.path.join(ncu_dir, name), exist_ok=True)
             out_dir = os.path.join(runtime_dir, name)
-            os.makedirs(out_dir, exist_ok=True)
+            if rank == 0:
+                os.makedirs(os.path.join(ncu_dir, name), exist_ok=True)
+                os.makedirs(out_dir, exist_ok=True)
             results = {}
             for n in sizes:
-                print("\nTesting configuration: Matrix Size=%d, Num Matrices=%d" % (n, batch))
+                if rank == 0:
+                    print("\nTesting configuration: Matrix Size=%d, Num Matrices=%d" % (n, batch))
                 template = api.read_template(a.input, n, dtype)
-                entry = run_config(n, batch, a.variant, dtype, template, a.runs, a.warm, a.cublas, a.peak_gbps)
-                print("Number of threads: %d" % entry["num_threads"])
-                results[result_key(n, batch, entry["num_threads"])] = entry
-                save_results(results, os.path.join(out_dir, "benchmark_results_%s.json" % name))
+                entry = run_config(n, batch, a.variant, dtype, template, a.runs, a.warm, a.cublas, a.peak_gbps, rank, world)
+                if rank == 0:
+                    print("Number of threads: %d" % entry["num_threads"])
+                    results[result_key(n, batch, entry["num_threads"])] = entry
+                    save_results(results, os.path.join(out_dir, "benchmark_results_%s.json" % name))
     except Exception as e:  # keep what we have, like the reference (run.py:252-260)
         print("Unexpected error: %s" % e)
-        save_results(results, os.path.join(runtime_dir, "benchmark_results_incomplete.json"))
+        if rank == 0:
+            save_results(results, os.path.join(runtime_dir, "benchmark_results_incomplete.json"))
         raise
+    finally:
+        if world > 1:
+            import torch.distributed as dist
+            if dist.is_initialized():
+                dist.destroy_process_group()
     return 0
 
 
