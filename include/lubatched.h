@@ -149,6 +149,11 @@ int lu_batched_read_tokens(const char* path, void* out, int64_t count, int dtype
 int lu_batched_replicate(const void* tmpl, void* dst, int n, int64_t batch, int dtype);
 
 /* Device facts (deviceProps.cu:4-23): SM count, max dynamic smem per block, clock kHz. */
+/* printMatrices / writeToFile (templated/verify.hpp:12-48): writes the FIRST matrix of the host buffer A
+ * (the reference loops break after k = 0) as text, default ostream formatting, one row per line, to
+ * `path`, or to stdout followed by an empty line when path is NULL. */
+int lu_batched_write_matrix(const void* A, const char* path, int n, int dtype);
+
 int lu_batched_device_info(int* sm_count, int* max_smem_optin, int* clock_khz, int* cc_major, int* cc_minor);
 
 const char* lu_batched_last_error(void);

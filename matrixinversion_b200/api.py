@@ -16,6 +16,7 @@ CPU fallback: the CUDA library must load and a GPU must be present for every com
 from __future__ import annotations
 
 import ctypes
+import os
 import sys
 import time
 from dataclasses import dataclass
@@ -257,6 +258,21 @@ def replicate(template: np.ndarray, batch: int) -> np.ndarray:
     out = np.empty((batch, n, n), dtype=template.dtype)
     check(_lib.lib().lu_batched_replicate(template.ctypes.data, out.ctypes.data, n, batch, _dtype_code(template.dtype)))
     return out
+
+
+def write_to_file(A, path: str) -> None:
+    """writeToFile (templated/verify.hpp:31-48): the first matrix of A[batch, n, n] (or A[n, n]) as text."""
+    A = np.ascontiguousarray(A)
+    first = A[0] if A.ndim == 3 else A
+    first = np.ascontiguousarray(first)
+    check(_lib.lib().lu_batched_write_matrix(first.ctypes.data, os.fsencode(path), first.shape[0], _dtype_code(first.dtype)))
+
+
+def print_matrices(A) -> None:
+    """printMatrices (templated/verify.hpp:12-29): the first matrix of A on stdout, then an empty line."""
+    A = np.ascontiguousarray(A)
+    first = np.ascontiguousarray(A[0] if A.ndim == 3 else A)
+    check(_lib.lib().lu_batched_write_matrix(first.ctypes.data, None, first.shape[0], _dtype_code(first.dtype)))
 
 
 def l1_norm(template: np.ndarray) -> float:

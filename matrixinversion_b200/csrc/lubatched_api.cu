@@ -10,6 +10,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <fstream>
+#include <iostream>
 #include <string>
 #include <vector>
 
@@ -380,6 +381,29 @@ int lu_batched_read_tokens(const char* path, void* out, int64_t count, int dtype
         else f >> static_cast<double*>(out)[i];
         if (!f) return fail(LUB_ERR_IO, std::string(path) + ": fewer tokens than requested");
     }
+    return LUB_OK;
+}
+
+// printMatrices / writeToFile (templated/verify.hpp:12-48): the FIRST matrix of the buffer only (both
+// reference loops `break` after k = 0), default ostream formatting, "value<space>" per entry, one row
+// per line; printMatrices adds an empty line after the matrix, writeToFile does not.
+int lu_batched_write_matrix(const void* A, const char* path, int n, int dtype) {
+    if (!A || n < 1) return fail(LUB_ERR_BAD_ARG, "bad arguments");
+    if (dtype != LUB_DTYPE_F32 && dtype != LUB_DTYPE_F64) return fail(LUB_ERR_BAD_DTYPE, "dtype must be 0 or 1");
+    std::ofstream file;
+    if (path) {
+        file.open(path);
+        if (!file) return fail(LUB_ERR_IO, std::string("cannot open ") + path);
+    }
+    std::ostream& os = path ? static_cast<std::ostream&>(file) : std::cout;
+    for (int i = 0; i < n; ++i) {
+        for (int j = 0; j < n; ++j) {
+            if (dtype == LUB_DTYPE_F32) os << static_cast<const float*>(A)[i * n + j] << ' ';
+            else os << static_cast<const double*>(A)[i * n + j] << ' ';
+        }
+        os << '\n';
+    }
+    if (!path) { os << '\n'; os.flush(); }
     return LUB_OK;
 }
 

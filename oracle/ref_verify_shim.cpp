@@ -63,6 +63,8 @@ void ref_verify_inv_f32(const float* A, const float* X, int n, int batch, long l
 void ref_verify_inv_f64(const double* A, const double* X, int n, int batch, long long* ok, long long* bad) { run_verify<double>(A, X, n, batch, ok, bad); }
 void ref_verify_lu_piv_f32(const float* PA, const float* LU, int n, int batch, long long* ok, long long* bad) { run_verify_lu<float>(PA, LU, n, batch, ok, bad); }
 void ref_verify_lu_piv_f64(const double* PA, const double* LU, int n, int batch, long long* ok, long long* bad) { run_verify_lu<double>(PA, LU, n, batch, ok, bad); }
+void ref_write_to_file_f32(const float* A, const char* path, int n, int batch) { std::vector<float> a(A, A + (size_t)n * n * batch); writeToFile<float>(a, path, n, batch); }
+void ref_write_to_file_f64(const double* A, const char* path, int n, int batch) { std::vector<double> a(A, A + (size_t)n * n * batch); writeToFile<double>(a, path, n, batch); }
 void ref_pivotedA_f32(const float* A, float* PA, int32_t* piv, int n) { run_pivoted<float>(A, PA, piv, n); }
 void ref_pivotedA_f64(const double* A, double* PA, int32_t* piv, int n) { run_pivoted<double>(A, PA, piv, n); }
 double ref_calc_cond_num_f32(const float* A, int n) { std::vector<float> a(A, A + (size_t)n * n); return (double)calc_cond_num<float>(a, n); }

@@ -169,6 +169,35 @@ def test_host_verify_lu_equals_reference_verdicts(inputs):
     assert np.isnan(lub.verify_lu(A, LU)[2])
 
 
+def test_write_to_file_matches_the_reference_text(tmp_path, inputs, capfd):
+    """writeToFile / printMatrices (templated/verify.hpp:12-48): first matrix only, default ostream
+    formatting; byte-identical to the reference's own function when oracle/_ref is present."""
+    for dt in (np.float32, np.float64):
+        A = np.stack([template(inputs, "mtrand32_new1", 5, dt), template(inputs, "mtrand32", 5, dt)])
+        A[0, 0, 0] = 1e-7
+        A[0, 1, 1] = 123456789.0
+        p = tmp_path / "ours.txt"
+        lub.write_to_file(A, str(p))
+        text = p.read_text()
+        rows = text.split("\n")
+        assert len(rows) == 6 and rows[-1] == "" and all(r.endswith(" ") and len(r.split()) == 5 for r in rows[:5])
+        assert rows[0].split()[0] == "1e-07" and rows[1].split()[1] == "1.23457e+08"
+        assert np.allclose(np.array(text.split(), dtype=np.float64).reshape(5, 5), A[0], rtol=1e-5)
+        if O.have_ref("ref_verify"):
+            import ctypes as C
+            ref = C.CDLL(os.path.join(ROOT, "oracle", "_ref", "libref_verify.so"))
+            f = getattr(ref, "ref_write_to_file_" + ("f32" if dt == np.float32 else "f64"))
+            f.restype = None
+            f.argtypes = [C.c_void_p, C.c_char_p, C.c_int, C.c_int]
+            q = tmp_path / "ref.txt"
+            Ac = np.ascontiguousarray(A)
+            f(Ac.ctypes.data, str(q).encode(), 5, 2)
+            assert q.read_bytes() == p.read_bytes()
+    lub.print_matrices(A)
+    out = capfd.readouterr().out
+    assert out == text + "\n"
+
+
 def test_default_num_threads_table():
     """templated/run.py:201-223."""
     table = {1: 32, 2: 32, 3: 30, 4: 32, 5: 30, 6: 30, 7: 28, 8: 32, 9: 27, 10: 30, 11: 22, 12: 24, 13: 26,
