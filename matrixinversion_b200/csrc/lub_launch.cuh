@@ -98,6 +98,12 @@ constexpr int pick_minb(int n, int es, bool pivoting) {
     return 2;
 }
 
+// Per-tile block barrier of lub_v3_kernel (keeps a block's warps on the same stretch of straight-line code):
+// pays from the sizes on whose unrolled code outgrows the instruction caches -- N >= 24, and N >= 18 with
+// the position-wise pivot search of the parallel mode; below that it costs 4-6 % (13 % at N = 23 without
+// pivoting), profiles/r01_tune_late.jsonl "bsync" sweep.
+constexpr bool pick_bsync(int n, int mode) { return n >= 24 || (mode == kModeParallel && n >= 18); }
+
 template <typename T, int N, int MODE>
 struct V3Cfg {
 #if defined(LUB_FORCE_GR) && defined(LUB_FORCE_GC)
@@ -108,6 +114,7 @@ struct V3Cfg {
 #endif
     // resident 256-thread blocks per SM the kernel is compiled for (register cap 128 / 80 / 64 per thread)
     static constexpr int MINB = pick_minb(N, (int)sizeof(T), MODE != kModeNone);
+    static constexpr bool BSYNC = pick_bsync(N, MODE);
 };
 
 #ifndef LUB_USE_TMA
@@ -243,7 +250,8 @@ cudaError_t launch(void* A, int32_t* piv, long long batch, int threads, cudaStre
     // no pivoting on the 16-byte image: the next tile is prefetched with cp.async while this one is
     // eliminated and the results leave straight from the registers (12-22 % faster, N = 16..24,
     // profiles/r01_tune_prefetch.jsonl); no per-tile block barrier there
-    constexpr bool V3_PF = !USE_V4 && (MODE == kModeNone) && V3Layout<T, N, VC::GR, VC::GC, MODE>::ROWVEC;
+    // (below N = 12 the tiles are so small that the plain path wins: N = 8 0.129 -> 0.100 ms)
+    constexpr bool V3_PF = !USE_V4 && (MODE == kModeNone) && V3Layout<T, N, VC::GR, VC::GC, MODE>::ROWVEC && N >= 12;
     if (fast) {
         mpw = FL::MPW; g = FL::G; c = &cache_fast[dev];
         if constexpr (USE_V4) {
@@ -254,7 +262,7 @@ cudaError_t launch(void* A, int32_t* piv, long long batch, int threads, cudaStre
             err = prepare(lub_v3_kernel<T, N, VC::GR, VC::GC, MODE, VC::MINB, false, 0, true>, *c, dev, threads, smem);
         } else {
             smem = FL::HEADER_BYTES + warps * FL::WARP_BYTES;
-            err = prepare(lub_v3_kernel<T, N, VC::GR, VC::GC, MODE, VC::MINB>, *c, dev, threads, smem);
+            err = prepare(lub_v3_kernel<T, N, VC::GR, VC::GC, MODE, VC::MINB, VC::BSYNC>, *c, dev, threads, smem);
         }
     } else {
         smem = GL::HEADER_BYTES + warps * GL::WARP_BYTES; mpw = GL::MPW; g = GL::G; c = &cache_gen[dev];
@@ -285,7 +293,7 @@ cudaError_t launch(void* A, int32_t* piv, long long batch, int threads, cudaStre
             lub_v3_kernel<T, N, VC::GR, VC::GC, MODE, VC::MINB, false, 0, true>
                 <<<(unsigned)blocks, threads, smem, stream>>>(static_cast<T*>(A), piv, batch);
         else
-            lub_v3_kernel<T, N, VC::GR, VC::GC, MODE, VC::MINB>
+            lub_v3_kernel<T, N, VC::GR, VC::GC, MODE, VC::MINB, VC::BSYNC>
                 <<<(unsigned)blocks, threads, smem, stream>>>(static_cast<T*>(A), piv, batch);
     } else
         lub_invert_kernel<T, N, AutoCfg<T, N, MODE>::GR, AutoCfg<T, N, MODE>::GC, MODE>
