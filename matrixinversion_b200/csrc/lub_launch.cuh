@@ -91,7 +91,7 @@ constexpr Cfg pick_v3_cfg(int n, int es, bool pivoting) {
 // search): more resident warps win 10-20 % there (profiles/r01_tune_late.jsonl, "minb" sweep).  From N = 13
 // on the register cap of three blocks per SM spills.
 constexpr int pick_minb(int n, int es, bool pivoting) {
-    if (es != 4) return 2;
+    if (es != 4) return (n == 7 || n == 8) ? 3 : 2;  // fp64: 10-15 % at N = 7, 8; spills from N = 10 on
     if (n <= 6) return 4;
     if (n == 7 || (n >= 9 && n <= 11)) return 3;
     if (n == 12 && pivoting) return 3;
