@@ -301,7 +301,12 @@ int lu_batched_inplace_host(void* host_ptr, int32_t* host_piv, int n, int64_t ba
     if (!host_ptr) return fail(LUB_ERR_BAD_ARG, "host_ptr is NULL");
     const size_t mat_bytes = (size_t)n * n * esize(dtype);
     // ~64 MiB chunks, a whole number of matrices, at least 3 chunks in flight when possible
-    int64_t chunk = std::max<int64_t>(1, (int64_t)((64ull << 20) / mat_bytes));
+    static const unsigned long long chunk_mib = []() -> unsigned long long {  // tuning knob, default 64 MiB
+        const char* e = std::getenv("LUB_HOST_CHUNK_MIB");
+        const long v = e ? std::atol(e) : 0;
+        return (v >= 1 && v <= 4096) ? (unsigned long long)v : 64ull;
+    }();
+    int64_t chunk = std::max<int64_t>(1, (int64_t)((chunk_mib << 20) / mat_bytes));
     chunk = std::min<int64_t>(chunk, std::max<int64_t>(1, (batch + HostPipe::kSlots - 1) / HostPipe::kSlots));
     int dev = 0;
     CU(cudaGetDevice(&dev));
