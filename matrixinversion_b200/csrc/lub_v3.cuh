@@ -50,6 +50,9 @@ constexpr ScStrides pick_sc_strides(int n, int gr, int gc, int cm, int ew) {
 #ifndef LUB_V3_VECPIV
 #define LUB_V3_VECPIV 1
 #endif
+#ifndef LUB_V3_DENSE_MIN_N
+#define LUB_V3_DENSE_MIN_N 9
+#endif
 
 template <typename T, int N, int GR, int GC, int MODE>
 struct V3Layout {
@@ -64,7 +67,11 @@ struct V3Layout {
     // granularity pads LC and the extra FMA work costs more than the staging saves -- N=24: +12 %)
     static constexpr bool VECPIV = (LUB_V3_VECPIV != 0) && MODE != kModeNone && N > 16 && CHV == EPV &&
                                    ((N / EPV) % GC) == 0 && rowwise_prepass_ok(N, MODE);
-    static constexpr bool SC = (MODE != kModeNone) && !VECPIV;  // element-granular image, odd row stride
+    // Odd N: the dense image (row stride N) already has an odd stride, so the pivot modes stage it with the
+    // plain 128-bit span copy instead of the element scatter (which costs ~500 instructions per matrix at
+    // N = 31 and 3-way conflicts on its stores, profiles/r01_tune_v6.md section 5).
+    static constexpr bool DENSE = (MODE != kModeNone) && !VECPIV && (N % 2 == 1) && N >= LUB_V3_DENSE_MIN_N;
+    static constexpr bool SC = (MODE != kModeNone) && !VECPIV && !DENSE;  // element-granular image, odd row stride
     static constexpr int CH = SC ? 1 : CHV;
     static constexpr int G = GR * GC;
     static_assert(G >= 1 && G <= 32 && (32 % G) == 0, "G must divide 32");

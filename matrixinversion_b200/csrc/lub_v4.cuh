@@ -18,6 +18,10 @@
 #pragma once
 #include "lub_v3.cuh"
 
+#ifndef LUB_V4_DENSE
+#define LUB_V4_DENSE 1
+#endif
+
 namespace lub {
 
 // worst bank multiplicity of one warp-wide scalar access where lane (ml, gr, gc) touches
@@ -66,7 +70,13 @@ struct V4Layout {
     static constexpr int LR = cdiv_(N, GR);  // local rows:    i = li * GR + gr
     static constexpr int LC = cdiv_(N, GC);  // local columns: j = lj * GC + gc
     static constexpr int GM = GR < GC ? GR : GC;  // steps that share one code body
-    static constexpr Strides S = pick_strides(N, GR, GC, EW, MODE != kModeNone);
+    static constexpr Strides S0 = pick_strides(N, GR, GC, EW, MODE != kModeNone);
+    // Dense image (row stride N, no padding): staged with the plain 128-bit span copy instead of the
+    // element scatter.  Taken when it is as conflict-free for the register load as the best padded
+    // layout and -- with a pivot search walking columns -- N is odd (profiles/r01_tune_v6.md, section 5).
+    static constexpr bool DENSE = (LUB_V4_DENSE != 0) && (MODE == kModeNone || (N % 2 == 1)) &&
+                                  load_conflict(N, N * N, GR, GC, EW) <= load_conflict(S0.p, S0.ms, GR, GC, EW);
+    static constexpr Strides S = DENSE ? Strides{N, N * N} : S0;
     static constexpr int P = S.p, MS = S.ms, MPAD = MS - N * P;
     static constexpr bool ALIGNED = ((MPW * N * N * ES) % 16) == 0;
     static constexpr int IMG_BYTES = roundup_(MPW * MS * ES, 16) + 16;
@@ -145,7 +155,12 @@ lub_v4_kernel(T* __restrict__ A, int32_t* __restrict__ piv, long long batch) {
         const int nm = (batch - first < MPW) ? (int)(batch - first) : MPW;
         T* gspan = A + first * (long long)(N * N);
         T* img = reinterpret_cast<T*>(wbase);
-        if (!((DBG & 4) && tbase >= (long long)gridDim.x * nwarps)) copy_in_scatter<T, L, N>(img, gspan, nm * N * N, lane);
+        if constexpr (L::DENSE) {  // the image is the span itself, shifted so that 16-byte chunks line up
+            img = reinterpret_cast<T*>(wbase + (unsigned)(reinterpret_cast<uintptr_t>(gspan) & 15u));
+            if (!((DBG & 4) && tbase >= (long long)gridDim.x * nwarps)) copy_in<T>(img, gspan, nm * N * N, nm * N * N, lane);
+        } else {
+            if (!((DBG & 4) && tbase >= (long long)gridDim.x * nwarps)) copy_in_scatter<T, L, N>(img, gspan, nm * N * N, lane);
+        }
         __syncwarp();
 
         T* mimg = img + ml * MS;
@@ -250,7 +265,11 @@ lub_v4_kernel(T* __restrict__ A, int32_t* __restrict__ piv, long long batch) {
                 if (rok && pcol[lj] >= 0) mimg[i * P + pcol[lj]] = a[li][lj] * sc;
         }
         __syncwarp();
-        if (!((DBG & 4) && tbase >= (long long)gridDim.x * nwarps)) copy_out_gather<T, L, N>(gspan, img, nm * N * N, lane);
+        if constexpr (L::DENSE) {
+            if (!((DBG & 4) && tbase >= (long long)gridDim.x * nwarps)) copy_out<T>(gspan, img, nm * N * N, lane);
+        } else {
+            if (!((DBG & 4) && tbase >= (long long)gridDim.x * nwarps)) copy_out_gather<T, L, N>(gspan, img, nm * N * N, lane);
+        }
         int32_t* pivp = piv;
         asm volatile("" : "+l"(pivp));  // opaque: keeps the compiler from cloning the whole tile loop on piv == NULL
         if (pivp != nullptr) {
