@@ -50,6 +50,9 @@ constexpr ScStrides pick_sc_strides(int n, int gr, int gc, int cm, int ew) {
 #ifndef LUB_V3_VECPIV
 #define LUB_V3_VECPIV 1
 #endif
+#ifndef LUB_V3_DENSE_EVEN
+#define LUB_V3_DENSE_EVEN 1
+#endif
 #ifndef LUB_V3_DENSE_MIN_N
 #define LUB_V3_DENSE_MIN_N 9
 #endif
@@ -68,9 +71,12 @@ struct V3Layout {
     static constexpr bool VECPIV = (LUB_V3_VECPIV != 0) && MODE != kModeNone && N > 16 && CHV == EPV &&
                                    ((N / EPV) % GC) == 0 && rowwise_prepass_ok(N, MODE);
     // Odd N: the dense image (row stride N) already has an odd stride, so the pivot modes stage it with the
-    // plain 128-bit span copy instead of the element scatter (which costs ~500 instructions per matrix at
-    // N = 31 and 3-way conflicts on its stores, profiles/r01_tune_v6.md section 5).
-    static constexpr bool DENSE = (MODE != kModeNone) && !VECPIV && (N % 2 == 1) && N >= LUB_V3_DENSE_MIN_N;
+    // plain 128-bit span copy instead of the element scatter (which costs ~700 instructions per matrix at
+    // N = 31 and 3-way conflicts on its stores, profiles/r01_tune_v6.md section 5).  N = 2 mod 4: the
+    // dense stride gives 2-way conflicts on the column walks of the pivot search, still cheaper than the
+    // scatter (N = 30 parallel 4.32 -> 3.19 ms); N = 0 mod 4 keeps the padded image (4-way and worse).
+    static constexpr bool DENSE = (MODE != kModeNone) && !VECPIV && N >= LUB_V3_DENSE_MIN_N &&
+                                  ((N % 2 == 1) || (LUB_V3_DENSE_EVEN >= 1 && N % 4 == 2) || (LUB_V3_DENSE_EVEN >= 2));
     static constexpr bool SC = (MODE != kModeNone) && !VECPIV && !DENSE;  // element-granular image, odd row stride
     static constexpr int CH = SC ? 1 : CHV;
     static constexpr int G = GR * GC;
