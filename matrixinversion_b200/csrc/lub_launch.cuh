@@ -104,6 +104,14 @@ constexpr int pick_minb(int n, int es, bool pivoting) {
 // pivoting), profiles/r01_tune_late.jsonl "bsync" sweep.
 constexpr bool pick_bsync(int n, int mode) { return n >= 24 || (mode == kModeParallel && n >= 18); }
 
+// Double-buffered cp.async prefetch of the dense pivot-mode image (lub_v3_kernel PFD): where it was measured
+// to win (5-16 %, profiles/r01_tune_late.jsonl "pfd"); at N = 15, 21, 30 the second image costs a resident block.
+constexpr bool pick_pfd(int n, int es, int mode) {
+    if (es != 4 || mode == kModeNone) return false;
+    if (n == 9 || n == 10 || n == 11 || n == 13 || n == 14 || n == 17) return true;
+    return (n == 18 || n == 19) && mode == kModeSerial;
+}
+
 template <typename T, int N, int MODE>
 struct V3Cfg {
 #if defined(LUB_FORCE_GR) && defined(LUB_FORCE_GC)
@@ -252,9 +260,13 @@ cudaError_t launch(void* A, int32_t* piv, long long batch, int threads, cudaStre
     // profiles/r01_tune_prefetch.jsonl); no per-tile block barrier there
     // (below N = 12 the tiles are so small that the plain path wins: N = 8 0.129 -> 0.100 ms)
     constexpr bool V3_PF = !USE_V4 && (MODE == kModeNone) && V3Layout<T, N, VC::GR, VC::GC, MODE>::ROWVEC && N >= 12;
+    constexpr bool V3_PFD = !USE_V4 && pick_pfd(N, (int)sizeof(T), MODE);
     if (fast) {
         mpw = FL::MPW; g = FL::G; c = &cache_fast[dev];
-        if constexpr (USE_V4) {
+        if constexpr (V3_PFD) {
+            smem = FL::HEADER_BYTES + warps * FL::WARP_BYTES_PFD;
+            err = prepare(lub_v3_kernel<T, N, VC::GR, VC::GC, MODE, VC::MINB, VC::BSYNC, 0, false, true>, *c, dev, threads, smem);
+        } else if constexpr (USE_V4) {
             smem = FL::HEADER_BYTES + warps * FL::WARP_BYTES;
             err = prepare(lub_v4_kernel<T, N, VC::GR, VC::GC, MODE, VC::MINB, false, 0>, *c, dev, threads, smem);
         } else if constexpr (V3_PF) {
@@ -286,7 +298,10 @@ cudaError_t launch(void* A, int32_t* piv, long long batch, int threads, cudaStre
     }
     if (dry_run || batch == 0) return cudaSuccess;
     if (fast) {
-        if constexpr (USE_V4)
+        if constexpr (V3_PFD)
+            lub_v3_kernel<T, N, VC::GR, VC::GC, MODE, VC::MINB, VC::BSYNC, 0, false, true>
+                <<<(unsigned)blocks, threads, smem, stream>>>(static_cast<T*>(A), piv, batch);
+        else if constexpr (USE_V4)
             lub_v4_kernel<T, N, VC::GR, VC::GC, MODE, VC::MINB, false, 0>
                 <<<(unsigned)blocks, threads, smem, stream>>>(static_cast<T*>(A), piv, batch);
         else if constexpr (V3_PF)

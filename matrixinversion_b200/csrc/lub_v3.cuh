@@ -103,6 +103,7 @@ struct V3Layout {
     // prefetching kernel: + a one-matrix output buffer (pivot modes only)
     static constexpr int OUT_BYTES = (MODE != kModeNone) ? roundup_(MS * ES, 16) : 0;
     static constexpr int WARP_BYTES_PF = IMG_BYTES + OUT_BYTES + PERM_BYTES;
+    static constexpr int WARP_BYTES_PFD = 2 * IMG_BYTES + PERM_BYTES;  // dense image, double-buffered (PFD)
     static constexpr int HEADER_BYTES = 64;
     static constexpr int CPR16 = N * ES / 16;
     static constexpr int RPAD16 = (P - N) * ES / 16, MPAD16 = MPAD * ES / 16;
@@ -182,6 +183,21 @@ __device__ __forceinline__ void copy_out_gather(T* __restrict__ dst, const T* __
     if (lane < total - tb) dst[tb + lane] = img[sc_off<L, N>(tb + lane)];
 }
 
+// Dense span copy global -> image with cp.async (no registers, the warp does not wait): 16-byte chunks, and
+// 4-byte pieces for a tail that is not a chunk multiple (a partial last tile of odd-N matrices).  The span
+// must start on 16 bytes (V3Layout::ALIGNED tiles of a 16-byte aligned batch).
+__device__ __forceinline__ void cp_async4(void* smem_dst, const void* gsrc) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
+}
+template <typename T>
+__device__ __forceinline__ void copy_in_dense_async(unsigned char* __restrict__ img, const T* __restrict__ src, int total, int lane) {
+    const int bytes = total * (int)sizeof(T);
+    const int nvec = bytes / 16;
+    const unsigned char* s = reinterpret_cast<const unsigned char*>(src);
+    for (int q = lane; q < nvec; q += 32) cp_async16(img + q * 16, s + q * 16);
+    for (int b = nvec * 16 + lane * 4; b < bytes; b += 128) cp_async4(img + b, s + b);
+}
+
 // BSYNC: one block barrier per tile (see the loop).  DBG (tuning harness only): 1 = skip the
 // elimination, 2 = skip the pivot pre-pass (identity permutation), 4 = skip global loads/stores
 // after the first tile.  DBG is 0 in the product.
@@ -234,11 +250,16 @@ __device__ __forceinline__ void gj_eliminate(T (&a)[LR][LC], T (&dinv)[LR], int 
 // HBM for its input.  The results then leave through a separate one-matrix output buffer, one
 // matrix of the tile at a time (pivot modes: the column scatter needs shared memory), or straight
 // from the registers (no pivoting: every lane owns whole 32-byte sectors of its rows).
-template <typename T, int N, int GR, int GC, int MODE, int MINB = 1, bool BSYNC = true, int DBG = 0, bool PF = false>
+// PFD (dense image of the pivot modes, V3Layout::DENSE && ALIGNED): two images per warp; the next tile is
+// fetched with cp.async into the idle one while this tile is searched, eliminated and written back from
+// the other -- the pivot modes need their image until the very end (column scatter), so the in-place
+// prefetch of PF does not apply.
+template <typename T, int N, int GR, int GC, int MODE, int MINB = 1, bool BSYNC = true, int DBG = 0, bool PF = false, bool PFD = false>
 __global__ void __launch_bounds__(kMaxThreads, MINB)
 lub_v3_kernel(T* __restrict__ A, int32_t* __restrict__ piv, long long batch) {
     using L = V3Layout<T, N, GR, GC, MODE>;
     static_assert(!PF || L::ROWVEC, "prefetch needs the 16-byte image");
+    static_assert(!PFD || (L::DENSE && L::ALIGNED && !PF), "double-buffered prefetch: dense image, 16-byte aligned tile spans");
     constexpr int G = L::G, MPW = L::MPW, LR = L::LR, LC = L::LC, CH = L::CH, CPL = L::CPL, CPR = L::CPR;
     constexpr int P = L::P, MS = L::MS;
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -247,9 +268,10 @@ lub_v3_kernel(T* __restrict__ A, int32_t* __restrict__ piv, long long batch) {
     const int warp = threadIdx.x >> 5;
     const int nwarps = blockDim.x >> 5;
     int8_t* slot_rank = reinterpret_cast<int8_t*>(smem_raw);
-    unsigned char* wbase = smem_raw + L::HEADER_BYTES + (size_t)warp * (PF ? L::WARP_BYTES_PF : L::WARP_BYTES);
-    unsigned char* obase = wbase + L::IMG_BYTES;  // PF: one-matrix output buffer
-    int* perm_all = reinterpret_cast<int*>(wbase + L::IMG_BYTES + (PF ? L::OUT_BYTES : 0));
+    unsigned char* wbase = smem_raw + L::HEADER_BYTES + (size_t)warp * (PF ? L::WARP_BYTES_PF : (PFD ? L::WARP_BYTES_PFD : L::WARP_BYTES));
+    unsigned char* obase = wbase + L::IMG_BYTES;  // PF: one-matrix output buffer; PFD: the second image
+    int* perm_all = reinterpret_cast<int*>(wbase + L::IMG_BYTES + (PF ? L::OUT_BYTES : (PFD ? L::IMG_BYTES : 0)));
+    int cur = 0;  // PFD: which image holds the tile being worked on
 
     if (MODE == kModeParallel) {
         if (threadIdx.x < N) slot_rank[threadIdx.x] = (int8_t)tree_slot_rank(threadIdx.x, N);
@@ -273,6 +295,15 @@ lub_v3_kernel(T* __restrict__ A, int32_t* __restrict__ piv, long long batch) {
         }
         cp_async_commit();
     }
+    if constexpr (PFD) {
+        const long long t0 = (long long)blockIdx.x * nwarps + warp;
+        if (t0 < ntiles) {
+            const long long first0 = t0 * MPW;
+            const int nm0 = (batch - first0 < MPW) ? (int)(batch - first0) : MPW;
+            copy_in_dense_async<T>(wbase, A + first0 * (long long)(N * N), nm0 * N * N, lane);
+        }
+        cp_async_commit();
+    }
 #pragma unroll 1
     for (long long tbase = (long long)blockIdx.x * nwarps; tbase < ntiles; tbase += (long long)gridDim.x * nwarps) {
         // Re-align the block's warps once per tile: they all run the same ~50 KB of straight-line
@@ -287,6 +318,18 @@ lub_v3_kernel(T* __restrict__ A, int32_t* __restrict__ piv, long long batch) {
         if constexpr (PF) {
             img = reinterpret_cast<T*>(wbase);
             cp_async_wait<0>();  // this tile, requested one round ago
+        } else if constexpr (PFD) {
+            img = reinterpret_cast<T*>(cur ? obase : wbase);
+            cp_async_wait<0>();  // this tile, requested one round ago
+            __syncwarp();        // ... by every lane; and the other image's write-back (last round) is done
+            const long long nxt = tile + tstride;
+            if (nxt < ntiles) {
+                const long long firstn = nxt * MPW;
+                const int nmn = (batch - firstn < MPW) ? (int)(batch - firstn) : MPW;
+                copy_in_dense_async<T>(cur ? wbase : obase, A + firstn * (long long)(N * N), nmn * N * N, lane);
+            }
+            cp_async_commit();
+            cur ^= 1;
         } else if ((DBG & 4) && tile >= (long long)gridDim.x * nwarps) {
             img = reinterpret_cast<T*>(wbase);
         } else if constexpr (L::SC) {
