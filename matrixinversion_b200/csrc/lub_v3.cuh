@@ -50,6 +50,9 @@ constexpr ScStrides pick_sc_strides(int n, int gr, int gc, int cm, int ew) {
 #ifndef LUB_V3_VECPIV
 #define LUB_V3_VECPIV 1
 #endif
+#ifndef LUB_V3_VECPIV_MIN_N
+#define LUB_V3_VECPIV_MIN_N 16
+#endif
 #ifndef LUB_V3_DENSE_EVEN
 #define LUB_V3_DENSE_EVEN 1
 #endif
@@ -68,7 +71,8 @@ struct V3Layout {
     // search walks columns through a dynamic row and needs the element-granular odd-stride image.
     // (only when the 16-byte chunks split evenly over the lane columns: otherwise the chunk
     // granularity pads LC and the extra FMA work costs more than the staging saves -- N=24: +12 %)
-    static constexpr bool VECPIV = (LUB_V3_VECPIV != 0) && MODE != kModeNone && N > 16 && CHV == EPV &&
+    // (N = 16 included: 0.87 -> 0.66 ms in the pivot modes; N = 8 is mixed and keeps the group search)
+    static constexpr bool VECPIV = (LUB_V3_VECPIV != 0) && MODE != kModeNone && N >= LUB_V3_VECPIV_MIN_N && CHV == EPV &&
                                    ((N / EPV) % GC) == 0 && rowwise_prepass_ok(N, MODE);
     // Odd N: the dense image (row stride N) already has an odd stride, so the pivot modes stage it with the
     // plain 128-bit span copy instead of the element scatter (which costs ~700 instructions per matrix at
@@ -351,7 +355,7 @@ lub_v3_kernel(T* __restrict__ A, int32_t* __restrict__ piv, long long batch) {
             for (int e = lane; e < MPW * N; e += 32) perm_all[e] = e % N;
             __syncwarp();
         } else if (MODE != kModeNone) {
-            if (N > 16) {
+            if (N > 16 || L::VECPIV) {
                 constexpr int MI = (MPW < 4) ? MPW : 4;
 #pragma unroll 1
                 for (int m = 0; m < MPW; m += MI)
