@@ -104,12 +104,16 @@ constexpr int pick_minb(int n, int es, bool pivoting) {
 // pivoting), profiles/r01_tune_late.jsonl "bsync" sweep.
 constexpr bool pick_bsync(int n, int mode) { return n >= 24 || (mode == kModeParallel && n >= 18); }
 
-// Double-buffered cp.async prefetch of the dense pivot-mode image (lub_v3_kernel PFD): where it was measured
-// to win (5-16 %, profiles/r01_tune_late.jsonl "pfd"); at N = 15, 21, 30 the second image costs a resident block.
+// Double-buffered cp.async prefetch of the dense image (lub_v3_kernel PFD): where it was measured to win
+// (profiles/r01_tune_late.jsonl "pfd": without pivoting 10-29 % for N = 9..23, 27, 29; serial 3-12 %; parallel
+// 1-16 % up to N = 17).  At N = 15, 21, 30, 31 with a pivot search the second image costs a resident block;
+// multiples of 4 have their own 16-byte-image / TMA paths.
 constexpr bool pick_pfd(int n, int es, int mode) {
-    if (es != 4 || mode == kModeNone) return false;
-    if (n == 9 || n == 10 || n == 11 || n == 13 || n == 14 || n == 17) return true;
-    return (n == 18 || n == 19) && mode == kModeSerial;
+    if (es != 4) return false;
+    const bool small = n == 9 || n == 10 || n == 11 || n == 13 || n == 14 || n == 17;
+    if (mode == kModeParallel) return small;
+    if (mode == kModeSerial) return small || n == 18 || n == 19 || n == 23 || n == 27 || n == 29;
+    return small || n == 15 || n == 18 || n == 19 || n == 21 || n == 22 || n == 23 || n == 25 || n == 26 || n == 27 || n == 29;
 }
 
 template <typename T, int N, int MODE>

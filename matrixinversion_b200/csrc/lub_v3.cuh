@@ -188,18 +188,24 @@ __device__ __forceinline__ void copy_out_gather(T* __restrict__ dst, const T* __
 }
 
 // Dense span copy global -> image with cp.async (no registers, the warp does not wait): 16-byte chunks, and
-// 4-byte pieces for a tail that is not a chunk multiple (a partial last tile of odd-N matrices).  The span
-// must start on 16 bytes (V3Layout::ALIGNED tiles of a 16-byte aligned batch).
+// 4-byte pieces for a head / tail that is not a chunk multiple (odd-N tiles start 8 bytes off every other
+// tile; a partial last tile).  sizeof(T) is a multiple of 4, the batch pointer of sizeof(T).
 __device__ __forceinline__ void cp_async4(void* smem_dst, const void* gsrc) {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
 }
 template <typename T>
-__device__ __forceinline__ void copy_in_dense_async(unsigned char* __restrict__ img, const T* __restrict__ src, int total, int lane) {
+__device__ __forceinline__ void copy_in_dense_async(unsigned char* __restrict__ buf, const T* __restrict__ src, int total, int lane) {
+    // the image starts at buf + (src & 15), so that global and shared 16-byte chunks line up (as copy_in does)
+    const unsigned mis = (unsigned)(reinterpret_cast<uintptr_t>(src) & 15u);
     const int bytes = total * (int)sizeof(T);
-    const int nvec = bytes / 16;
+    int head = mis ? (int)(16u - mis) : 0;
+    if (head > bytes) head = bytes;
     const unsigned char* s = reinterpret_cast<const unsigned char*>(src);
-    for (int q = lane; q < nvec; q += 32) cp_async16(img + q * 16, s + q * 16);
-    for (int b = nvec * 16 + lane * 4; b < bytes; b += 128) cp_async4(img + b, s + b);
+    unsigned char* img = buf + mis;
+    if (lane * 4 < head) cp_async4(img + lane * 4, s + lane * 4);
+    const int nvec = (bytes - head) / 16;
+    for (int q = lane; q < nvec; q += 32) cp_async16(img + head + q * 16, s + head + q * 16);
+    for (int b = head + nvec * 16 + lane * 4; b < bytes; b += 128) cp_async4(img + b, s + b);
 }
 
 // BSYNC: one block barrier per tile (see the loop).  DBG (tuning harness only): 1 = skip the
@@ -254,7 +260,8 @@ __device__ __forceinline__ void gj_eliminate(T (&a)[LR][LC], T (&dinv)[LR], int 
 // HBM for its input.  The results then leave through a separate one-matrix output buffer, one
 // matrix of the tile at a time (pivot modes: the column scatter needs shared memory), or straight
 // from the registers (no pivoting: every lane owns whole 32-byte sectors of its rows).
-// PFD (dense image of the pivot modes, V3Layout::DENSE && ALIGNED): two images per warp; the next tile is
+// PFD (dense image: V3Layout::DENSE in the pivot modes, any N that is not a multiple of 4 without pivoting;
+// any alignment of the tile spans): two images per warp; the next tile is
 // fetched with cp.async into the idle one while this tile is searched, eliminated and written back from
 // the other -- the pivot modes need their image until the very end (column scatter), so the in-place
 // prefetch of PF does not apply.
@@ -263,7 +270,7 @@ __global__ void __launch_bounds__(kMaxThreads, MINB)
 lub_v3_kernel(T* __restrict__ A, int32_t* __restrict__ piv, long long batch) {
     using L = V3Layout<T, N, GR, GC, MODE>;
     static_assert(!PF || L::ROWVEC, "prefetch needs the 16-byte image");
-    static_assert(!PFD || (L::DENSE && L::ALIGNED && !PF), "double-buffered prefetch: dense image, 16-byte aligned tile spans");
+    static_assert(!PFD || (!L::SC && !L::ROWVEC && !PF), "double-buffered prefetch: dense image");
     constexpr int G = L::G, MPW = L::MPW, LR = L::LR, LC = L::LC, CH = L::CH, CPL = L::CPL, CPR = L::CPR;
     constexpr int P = L::P, MS = L::MS;
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -323,7 +330,7 @@ lub_v3_kernel(T* __restrict__ A, int32_t* __restrict__ piv, long long batch) {
             img = reinterpret_cast<T*>(wbase);
             cp_async_wait<0>();  // this tile, requested one round ago
         } else if constexpr (PFD) {
-            img = reinterpret_cast<T*>(cur ? obase : wbase);
+            img = reinterpret_cast<T*>((cur ? obase : wbase) + (unsigned)(reinterpret_cast<uintptr_t>(gspan) & 15u));
             cp_async_wait<0>();  // this tile, requested one round ago
             __syncwarp();        // ... by every lane; and the other image's write-back (last round) is done
             const long long nxt = tile + tstride;
