@@ -116,6 +116,15 @@ constexpr bool pick_pfd(int n, int es, int mode) {
     return small || n == 15 || n == 18 || n == 19 || n == 21 || n == 22 || n == 23 || n == 25 || n == 26 || n == 27 || n == 29;
 }
 
+// The same prefetch in the fp64 kernel (lub_v4_kernel PFD), odd N (the sizes whose image is dense in every
+// mode): without pivoting -10..-26 % for N = 7..21, pivot modes -7..-13 % for N = 7, 9, 13, 17, 19; N = 11, 15, 23
+// with a pivot search lose a resident block to the second image (profiles/r01_tune_late.jsonl "pfd64").
+constexpr bool pick_pfd64(int n, int mode) {
+    if (n % 2 == 0 || n < 7 || n > 21) return false;
+    if (mode == kModeNone) return true;
+    return n == 7 || n == 9 || n == 13 || n == 17 || n == 19 || (n == 21 && mode == kModeSerial);
+}
+
 template <typename T, int N, int MODE>
 struct V3Cfg {
 #if defined(LUB_FORCE_GR) && defined(LUB_FORCE_GC)
@@ -265,11 +274,15 @@ cudaError_t launch(void* A, int32_t* piv, long long batch, int threads, cudaStre
     // (below N = 12 the tiles are so small that the plain path wins: N = 8 0.129 -> 0.100 ms)
     constexpr bool V3_PF = !USE_V4 && (MODE == kModeNone) && V3Layout<T, N, VC::GR, VC::GC, MODE>::ROWVEC && N >= 12;
     constexpr bool V3_PFD = !USE_V4 && pick_pfd(N, (int)sizeof(T), MODE);
+    constexpr bool V4_PFD = USE_V4 && pick_pfd64(N, MODE);
     if (fast) {
         mpw = FL::MPW; g = FL::G; c = &cache_fast[dev];
         if constexpr (V3_PFD) {
             smem = FL::HEADER_BYTES + warps * FL::WARP_BYTES_PFD;
             err = prepare(lub_v3_kernel<T, N, VC::GR, VC::GC, MODE, VC::MINB, VC::BSYNC, 0, false, true>, *c, dev, threads, smem);
+        } else if constexpr (USE_V4 && V4_PFD) {
+            smem = FL::HEADER_BYTES + warps * FL::WARP_BYTES_PFD;
+            err = prepare(lub_v4_kernel<T, N, VC::GR, VC::GC, MODE, VC::MINB, false, 0, true>, *c, dev, threads, smem);
         } else if constexpr (USE_V4) {
             smem = FL::HEADER_BYTES + warps * FL::WARP_BYTES;
             err = prepare(lub_v4_kernel<T, N, VC::GR, VC::GC, MODE, VC::MINB, false, 0>, *c, dev, threads, smem);
@@ -304,6 +317,9 @@ cudaError_t launch(void* A, int32_t* piv, long long batch, int threads, cudaStre
     if (fast) {
         if constexpr (V3_PFD)
             lub_v3_kernel<T, N, VC::GR, VC::GC, MODE, VC::MINB, VC::BSYNC, 0, false, true>
+                <<<(unsigned)blocks, threads, smem, stream>>>(static_cast<T*>(A), piv, batch);
+        else if constexpr (USE_V4 && V4_PFD)
+            lub_v4_kernel<T, N, VC::GR, VC::GC, MODE, VC::MINB, false, 0, true>
                 <<<(unsigned)blocks, threads, smem, stream>>>(static_cast<T*>(A), piv, batch);
         else if constexpr (USE_V4)
             lub_v4_kernel<T, N, VC::GR, VC::GC, MODE, VC::MINB, false, 0>

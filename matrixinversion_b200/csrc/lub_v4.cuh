@@ -74,14 +74,16 @@ struct V4Layout {
     // Dense image (row stride N, no padding): staged with the plain 128-bit span copy instead of the
     // element scatter.  Taken when it is as conflict-free for the register load as the best padded
     // layout and -- with a pivot search walking columns -- N is odd (profiles/r01_tune_v6.md, section 5).
+    // (odd N: always -- measured 0..-9 % even where the conflict model prefers a padded layout)
     static constexpr bool DENSE = (LUB_V4_DENSE != 0) && (MODE == kModeNone || (N % 2 == 1)) &&
-                                  load_conflict(N, N * N, GR, GC, EW) <= load_conflict(S0.p, S0.ms, GR, GC, EW);
+                                  ((N % 2 == 1) || load_conflict(N, N * N, GR, GC, EW) <= load_conflict(S0.p, S0.ms, GR, GC, EW));
     static constexpr Strides S = DENSE ? Strides{N, N * N} : S0;
     static constexpr int P = S.p, MS = S.ms, MPAD = MS - N * P;
     static constexpr bool ALIGNED = ((MPW * N * N * ES) % 16) == 0;
     static constexpr int IMG_BYTES = roundup_(MPW * MS * ES, 16) + 16;
     static constexpr int PERM_BYTES = (MODE != kModeNone) ? roundup_(MPW * N * 4, 16) : 0;
     static constexpr int WARP_BYTES = IMG_BYTES + PERM_BYTES;
+    static constexpr int WARP_BYTES_PFD = 2 * IMG_BYTES + PERM_BYTES;  // dense image, double-buffered (PFD)
     static constexpr int HEADER_BYTES = 64;
 };
 
@@ -110,10 +112,13 @@ __device__ __forceinline__ void row_update_masked(double (&a)[LC], const double 
 }
 
 // DBG bit 16 (tuning): fully unroll the inner steps as well
-template <typename T, int N, int GR, int GC, int MODE, int MINB = 1, bool BSYNC = true, int DBG = 0>
+// PFD (dense layouts): two images per warp, the next tile is fetched with cp.async into the idle one while
+// this tile is worked on (see lub_v3_kernel).
+template <typename T, int N, int GR, int GC, int MODE, int MINB = 1, bool BSYNC = true, int DBG = 0, bool PFD = false>
 __global__ void __launch_bounds__(kMaxThreads, MINB)
 lub_v4_kernel(T* __restrict__ A, int32_t* __restrict__ piv, long long batch) {
     using L = V4Layout<T, N, GR, GC, MODE>;
+    static_assert(!PFD || L::DENSE, "double-buffered prefetch needs the dense image");
     constexpr int G = L::G, MPW = L::MPW, LR = L::LR, LC = L::LC, GM = L::GM, P = L::P, MS = L::MS;
     constexpr unsigned STAGGER_NS = (DBG >> 8) * 500u;  // tuning: DBG bits 8.. = stagger quantum in 0.5 us
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -122,8 +127,10 @@ lub_v4_kernel(T* __restrict__ A, int32_t* __restrict__ piv, long long batch) {
     const int warp = threadIdx.x >> 5;
     const int nwarps = blockDim.x >> 5;
     int8_t* slot_rank = reinterpret_cast<int8_t*>(smem_raw);
-    unsigned char* wbase = smem_raw + L::HEADER_BYTES + (size_t)warp * L::WARP_BYTES;
-    int* perm_all = reinterpret_cast<int*>(wbase + L::IMG_BYTES);
+    unsigned char* wbase = smem_raw + L::HEADER_BYTES + (size_t)warp * (PFD ? L::WARP_BYTES_PFD : L::WARP_BYTES);
+    unsigned char* obase = wbase + L::IMG_BYTES;  // PFD: the second image
+    int* perm_all = reinterpret_cast<int*>(wbase + (PFD ? 2 : 1) * L::IMG_BYTES);
+    int cur = 0;
 
     if (MODE == kModeParallel) {
         if (threadIdx.x < N) slot_rank[threadIdx.x] = (int8_t)tree_slot_rank(threadIdx.x, N);
@@ -144,6 +151,15 @@ lub_v4_kernel(T* __restrict__ A, int32_t* __restrict__ piv, long long batch) {
         const unsigned slot = BSYNC ? (blockIdx.x / 148u) % 4u : (unsigned)(warp + blockIdx.x) % 4u;
         if (slot) __nanosleep(slot * STAGGER_NS);
     }
+    if constexpr (PFD) {
+        const long long t0 = (long long)blockIdx.x * nwarps + warp;
+        if (t0 < ntiles) {
+            const long long first0 = t0 * MPW;
+            const int nm0 = (batch - first0 < MPW) ? (int)(batch - first0) : MPW;
+            copy_in_dense_async<T>(wbase, A + first0 * (long long)(N * N), nm0 * N * N, lane);
+        }
+        cp_async_commit();
+    }
 #pragma unroll 1
     for (long long tbase = (long long)blockIdx.x * nwarps; tbase < ntiles; tbase += (long long)gridDim.x * nwarps) {
         // Re-align the block's warps once per tile: they all run the same straight-line code, and
@@ -155,7 +171,19 @@ lub_v4_kernel(T* __restrict__ A, int32_t* __restrict__ piv, long long batch) {
         const int nm = (batch - first < MPW) ? (int)(batch - first) : MPW;
         T* gspan = A + first * (long long)(N * N);
         T* img = reinterpret_cast<T*>(wbase);
-        if constexpr (L::DENSE) {  // the image is the span itself, shifted so that 16-byte chunks line up
+        if constexpr (PFD) {
+            img = reinterpret_cast<T*>((cur ? obase : wbase) + (unsigned)(reinterpret_cast<uintptr_t>(gspan) & 15u));
+            cp_async_wait<0>();  // this tile, requested one round ago
+            __syncwarp();
+            const long long nxt = tile + (long long)gridDim.x * nwarps;
+            if (nxt < ntiles) {
+                const long long firstn = nxt * MPW;
+                const int nmn = (batch - firstn < MPW) ? (int)(batch - firstn) : MPW;
+                copy_in_dense_async<T>(cur ? wbase : obase, A + firstn * (long long)(N * N), nmn * N * N, lane);
+            }
+            cp_async_commit();
+            cur ^= 1;
+        } else if constexpr (L::DENSE) {  // the image is the span itself, shifted so that 16-byte chunks line up
             img = reinterpret_cast<T*>(wbase + (unsigned)(reinterpret_cast<uintptr_t>(gspan) & 15u));
             if (!((DBG & 4) && tbase >= (long long)gridDim.x * nwarps)) copy_in<T>(img, gspan, nm * N * N, nm * N * N, lane);
         } else {

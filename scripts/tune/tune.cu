@@ -38,17 +38,17 @@ template <typename T, int N, int GR, int GC, int MODE, int MINB, int DBG = 0>
 struct V {
     using L = V4Layout<T, N, GR, GC, MODE>;
     static void set_attr(int smem) {
-        cudaFuncSetAttribute(lub_v4_kernel<T, N, GR, GC, MODE, MINB, (DBG & 8) != 0, (DBG & ~8)>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        cudaFuncSetAttribute(lub_v4_kernel<T, N, GR, GC, MODE, MINB, (DBG & 8) != 0, (DBG & ~(8 | 32)), (DBG & 32) != 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     }
     static void launch(void* A, int* piv, long long batch, unsigned blocks, int threads, int smem, cudaStream_t s) {
-        lub_v4_kernel<T, N, GR, GC, MODE, MINB, (DBG & 8) != 0, (DBG & ~8)><<<blocks, threads, smem, s>>>((T*)A, piv, batch);
+        lub_v4_kernel<T, N, GR, GC, MODE, MINB, (DBG & 8) != 0, (DBG & ~(8 | 32)), (DBG & 32) != 0><<<blocks, threads, smem, s>>>((T*)A, piv, batch);
     }
     static int occ(int threads, int smem) {
         int o = 0;
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, lub_v4_kernel<T, N, GR, GC, MODE, MINB, (DBG & 8) != 0, (DBG & ~8)>, threads, smem);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, lub_v4_kernel<T, N, GR, GC, MODE, MINB, (DBG & 8) != 0, (DBG & ~(8 | 32)), (DBG & 32) != 0>, threads, smem);
         return o;
     }
-    static Variant make(const char* name) { return Variant{name, L::MPW, L::WARP_BYTES, L::HEADER_BYTES, set_attr, launch, occ}; }
+    static Variant make(const char* name) { return Variant{name, L::MPW, (DBG & 32) ? L::WARP_BYTES_PFD : L::WARP_BYTES, L::HEADER_BYTES, set_attr, launch, occ}; }
 };
 
 template <typename T, int N, int GR, int GC, int MODE, int NPW, int NCW, int NB, int PRE>
