@@ -120,6 +120,7 @@ constexpr bool pick_pfd(int n, int es, int mode) {
 // mode): without pivoting -10..-26 % for N = 7..21, pivot modes -7..-13 % for N = 7, 9, 13, 17, 19; N = 11, 15, 23
 // with a pivot search lose a resident block to the second image (profiles/r01_tune_late.jsonl "pfd64").
 constexpr bool pick_pfd64(int n, int mode) {
+    if (pick_dense_even(n, mode)) return true;  // fp64 N = 10, 14, 18, 20 without pivoting: -20..-27 % (dense + prefetch)
     if (n % 2 == 0 || n < 7 || n > 21) return false;
     if (mode == kModeNone) return true;
     return n == 7 || n == 9 || n == 13 || n == 17 || n == 19 || (n == 21 && mode == kModeSerial);

@@ -43,6 +43,10 @@ constexpr int load_conflict(int p, int ms, int gr_n, int gc_n, int ew) {
 
 struct Strides { int p, ms; };
 
+// even N without pivoting for which the dense image (+ prefetch) was measured to win although the conflict
+// model prefers a padded layout (filled from profiles/r01_tune_late.jsonl "pfd64 even")
+constexpr bool pick_dense_even(int n, int mode) { return mode == kModeNone && (n == 10 || n == 14 || n == 18 || n == 20); }
+
 // odd_only: the pivot search walks columns (row stride must be odd to be conflict-free); without
 // pivoting any stride will do and a conflict-free register load usually exists with an even one
 constexpr Strides pick_strides(int n, int gr, int gc, int ew, bool odd_only) {
@@ -76,7 +80,8 @@ struct V4Layout {
     // layout and -- with a pivot search walking columns -- N is odd (profiles/r01_tune_v6.md, section 5).
     // (odd N: always -- measured 0..-9 % even where the conflict model prefers a padded layout)
     static constexpr bool DENSE = (LUB_V4_DENSE != 0) && (MODE == kModeNone || (N % 2 == 1)) &&
-                                  ((N % 2 == 1) || load_conflict(N, N * N, GR, GC, EW) <= load_conflict(S0.p, S0.ms, GR, GC, EW));
+                                  ((N % 2 == 1) || LUB_V4_DENSE >= 2 || pick_dense_even(N, MODE) ||
+                                   load_conflict(N, N * N, GR, GC, EW) <= load_conflict(S0.p, S0.ms, GR, GC, EW));
     static constexpr Strides S = DENSE ? Strides{N, N * N} : S0;
     static constexpr int P = S.p, MS = S.ms, MPAD = MS - N * P;
     static constexpr bool ALIGNED = ((MPW * N * N * ES) % 16) == 0;
