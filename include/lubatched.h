@@ -91,8 +91,10 @@ int lu_batched_inplace_host(void* host_ptr, int32_t* host_piv, int n, int64_t ba
                             int dtype);
 
 /* NUMTHREADS knob (templated/luBatchedInplace.cu:6; table templated/run.py:201-223):
- * threads per block for subsequent launches, a multiple of 32 in [32, 256];
- * 0 restores the library's per-(n, dtype) default. */
+ * threads per block for subsequent launches of the calling thread, a multiple of 32 in [32, 256];
+ * 0 restores the library's per-(n, dtype, pivot_mode) default.  lu_batched_get_threads returns the
+ * value in force: the knob if set, else the library default for (n, dtype) with parallel pivoting
+ * (the reference's headline variant; other modes: lu_batched_geometry), -1 without a device. */
 int lu_batched_set_threads(int numthreads);
 int lu_batched_get_threads(int n, int dtype);
 
@@ -137,6 +139,12 @@ int lu_batched_verify_lu(const void* A, const void* LU, const int32_t* piv, int 
 int lu_batched_verify_inv_device(const void* dA, const void* dAinv, int n, int64_t batch, int dtype,
                                  double thr, int64_t* n_correct, int64_t* n_incorrect,
                                  double* max_abs_dev);
+
+/* Same on an explicit stream (a cudaStream_t passed as void*): does not touch the calling thread's
+ * lu_batched_set_stream setting. */
+int lu_batched_verify_inv_device_stream(const void* dA, const void* dAinv, int n, int64_t batch, int dtype,
+                                        double thr, int64_t* n_correct, int64_t* n_incorrect,
+                                        double* max_abs_dev, void* stream);
 
 /* Text input with the reference's semantics (templated/luBatchedInplace.cu:27-34): the
  * first `count` whitespace-separated tokens of `path`, parsed as T -- a PREFIX of the

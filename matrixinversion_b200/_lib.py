@@ -61,6 +61,7 @@ SIGNATURES = {
     "lu_batched_verify_inv": (ctypes.c_int, [_P, _P, ctypes.c_int, ctypes.c_int64, ctypes.c_int, ctypes.c_double, _I64P, _I64P, _DP]),
     "lu_batched_verify_lu": (ctypes.c_int, [_P, _P, _P, ctypes.c_int, ctypes.c_int64, ctypes.c_int, ctypes.c_double, _I64P, _I64P, _DP]),
     "lu_batched_verify_inv_device": (ctypes.c_int, [_P, _P, ctypes.c_int, ctypes.c_int64, ctypes.c_int, ctypes.c_double, _I64P, _I64P, _DP]),
+    "lu_batched_verify_inv_device_stream": (ctypes.c_int, [_P, _P, ctypes.c_int, ctypes.c_int64, ctypes.c_int, ctypes.c_double, _I64P, _I64P, _DP, _P]),
     "lu_batched_read_tokens": (ctypes.c_int, [ctypes.c_char_p, _P, ctypes.c_int64, ctypes.c_int]),
     "lu_batched_write_matrix": (ctypes.c_int, [_P, ctypes.c_char_p, ctypes.c_int, ctypes.c_int]),
     "lu_batched_replicate": (ctypes.c_int, [_P, _P, ctypes.c_int, ctypes.c_int64, ctypes.c_int]),

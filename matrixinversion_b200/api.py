@@ -95,6 +95,8 @@ def lu_batched_inplace(A, piv=None, pivot_mode="parallel", stream=None):
         if piv is not None:
             if not (piv.is_cuda and piv.is_contiguous() and piv.dtype == torch.int32 and tuple(piv.shape) == (batch, n)):
                 raise LubError(-4, "piv must be a contiguous CUDA int32 [batch, n] tensor")
+            if piv.device != A.device:
+                raise LubError(-4, "piv must live on A's device")
             pptr = piv.data_ptr()
         with torch.cuda.device(A.device):
             s = stream if stream is not None else torch.cuda.current_stream(A.device)
@@ -129,6 +131,8 @@ def lu_batched_factor_inplace(A, piv=None, pivot_mode="parallel", stream=None):
     if piv is not None:
         if not (piv.is_cuda and piv.is_contiguous() and piv.dtype == torch.int32 and tuple(piv.shape) == (batch, n)):
             raise LubError(-4, "piv must be a contiguous CUDA int32 [batch, n] tensor")
+        if piv.device != A.device:
+            raise LubError(-4, "piv must live on A's device")
         pptr = piv.data_ptr()
     with torch.cuda.device(A.device):
         s = stream if stream is not None else torch.cuda.current_stream(A.device)
@@ -225,11 +229,13 @@ def verify_inv(A, A_inv, thr: float = 1e-3):
         if not (A.is_cuda and A_inv.is_cuda and A.is_contiguous() and A_inv.is_contiguous() and A.dtype == A_inv.dtype):
             raise LubError(-4, "A and A_inv must be contiguous CUDA tensors of one dtype")
         import torch
+        if A_inv.device != A.device:
+            raise LubError(-4, "A and A_inv must live on the same device")
         with torch.cuda.device(A.device):
-            check(L.lu_batched_set_stream(torch.cuda.current_stream(A.device).cuda_stream))
-            check(L.lu_batched_verify_inv_device(A.data_ptr(), A_inv.data_ptr(), n, batch, _dtype_code(A.dtype), thr,
-                                                 ctypes.byref(ok), ctypes.byref(bad), ctypes.byref(dev)))
-            check(L.lu_batched_set_stream(None))
+            # explicit-stream entry point: the caller's lu_batched_set_stream setting stays untouched
+            check(L.lu_batched_verify_inv_device_stream(A.data_ptr(), A_inv.data_ptr(), n, batch, _dtype_code(A.dtype), thr,
+                                                        ctypes.byref(ok), ctypes.byref(bad), ctypes.byref(dev),
+                                                        torch.cuda.current_stream(A.device).cuda_stream))
     else:
         A = np.ascontiguousarray(A)
         A_inv = np.ascontiguousarray(A_inv, dtype=A.dtype)

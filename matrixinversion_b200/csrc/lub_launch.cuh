@@ -4,6 +4,8 @@
 // (parallel_pivot/luBatchedInplace.cu:8-11,118-127) and the NUMTHREADS table of its sweep
 // driver (templated/run.py:201-223).
 #pragma once
+#include <atomic>
+#include <mutex>
 #include <type_traits>
 #include "lub_kernel.cuh"
 #include "lub_fast.cuh"
@@ -27,7 +29,9 @@ struct LaunchInfo {
 // int launcher(A, piv, batch, threads (0 = default), stream, info (may be NULL), flags)
 // flags: bit 0 = dry run (fill `info`, launch nothing), bit 1 = LU factors only (no inversion)
 constexpr int kLaunchDryRun = 1, kLaunchLuOnly = 2;
-using LaunchFn = cudaError_t (*)(void*, int32_t*, long long, int, cudaStream_t, LaunchInfo*, int);
+// ev0 (may be NULL): recorded on the stream immediately before the kernel launch, i.e. after the one-time
+// preparation and the tensor-map encode, so that the ABI's "kernel execution time" is the kernel's
+using LaunchFn = cudaError_t (*)(void*, int32_t*, long long, int, cudaStream_t, LaunchInfo*, int, cudaEvent_t);
 
 // Lane layout choice.  A matrix is spread over G = GR x GC lanes, each holding an LR x LC
 // block in registers.  Smallest G whose block fits the per-lane element budget wins (fewer
@@ -153,16 +157,25 @@ constexpr bool kUseTma = LUB_USE_TMA != 0;
 //     plus parallel pivoting at N = 24; elsewhere the position-wise pivot search on the swizzled image
 //     (4-way bank conflicts on its column walk) loses to the odd-stride image of lub_v3.cuh.  Smaller N
 //     would need a padded image too large for two blocks per SM.
-struct TmaChoice { bool on; int gr, gc; bool bsync; };
+// `opt`: kTmaLean | kTmaDB (lub_tma.cuh); `maxt`: block size the kernel is compiled for; `threads`: the library's
+// default block size for the configuration.  Round-2 measurements (profiles/r02_tune_headline.jsonl):
+//   * N = 32 fp32, pivot modes: lean step + two images per warp, one 384-thread block per SM, no per-tile barrier:
+//     2.62 -> 2.33 ms (parallel), 2.71 -> 2.51 ms (serial);
+//   * N = 32 fp32 without pivoting: the same with the image output path, 256 threads: 2.35 -> 2.07 ms;
+//   * N = 16 fp64, pivot modes: two images per warp, two 192-thread blocks per SM: 1.34 -> 1.23 ms;
+//   * N = 24 / 28 fp32 and N = 32 fp64: no gain from either (second image costs resident warps), unchanged.
+struct TmaChoice { bool on; int gr, gc; bool bsync; int opt; int maxt; int threads; };
 constexpr TmaChoice pick_tma(int n, int es, int mode, Cfg v3) {
     const int rowb = n * es;
     const bool piv = mode != kModeNone;
-    if (rowb == 128) return TmaChoice{true, v3.gr, v3.gc, piv};
-    if (rowb == 256) return TmaChoice{piv, v3.gr, v3.gc, true};
-    if (es == 4 && n == 20) return TmaChoice{mode != kModeParallel, 4, 2, piv};
-    if (es == 4 && n == 24) return TmaChoice{true, 8, 2, mode == kModeParallel};
-    if (es == 4 && n == 28) return TmaChoice{mode != kModeParallel, 4, 4, false};
-    return TmaChoice{false, v3.gr, v3.gc, false};
+    if (es == 4 && n == 32) return TmaChoice{true, v3.gr, v3.gc, false, kTmaLean | kTmaDB, 384, piv ? 384 : 256};
+    if (es == 8 && n == 16 && piv) return TmaChoice{true, v3.gr, v3.gc, true, kTmaDB, 384, 192};
+    if (rowb == 128) return TmaChoice{true, v3.gr, v3.gc, piv, 0, kMaxThreads, 256};
+    if (rowb == 256) return TmaChoice{piv, v3.gr, v3.gc, true, 0, kMaxThreads, 256};
+    if (es == 4 && n == 20) return TmaChoice{mode != kModeParallel, 4, 2, piv, 0, kMaxThreads, 256};
+    if (es == 4 && n == 24) return TmaChoice{true, 8, 2, mode == kModeParallel, 0, kMaxThreads, 256};
+    if (es == 4 && n == 28) return TmaChoice{mode != kModeParallel, 4, 4, false, 0, kMaxThreads, 256};
+    return TmaChoice{false, v3.gr, v3.gc, false, 0, kMaxThreads, 256};
 }
 template <typename T, int N, int MODE>
 struct TmaCfg {
@@ -170,62 +183,122 @@ struct TmaCfg {
     static constexpr bool ON = kUseTma && c.on;
     static constexpr int GR = c.gr, GC = c.gc;
     static constexpr bool BSYNC = c.bsync;
+    static constexpr int OPT = c.opt, MAXT = c.maxt, THREADS = c.threads;
 };
 
 constexpr int kMaxDevices = 64;
+constexpr int kMaxWarps = 16;
 
-struct KernelCache { int ready_threads; int blocks_per_sm; int sms; int regs; };
+// Per-(kernel instantiation, device) launch facts, filled once and read by any number of host threads
+// (thread-safe for distinct streams / devices).  The dynamic shared memory opt-in is set ONCE,
+// to the size of the largest block the kernel is compiled for, so a thread that lowered the NUMTHREADS knob
+// cannot shrink it under another thread's launch; occupancy is cached per block size and published with a
+// release store after the entry is complete.
+struct KernelCache {
+    std::mutex mu;
+    bool attr_set = false;
+    int sms = 0, regs = 0;
+    std::atomic<int> occ[kMaxWarps + 1];
+    KernelCache() { for (auto& o : occ) o.store(0, std::memory_order_relaxed); }
+};
 
 template <typename K>
-cudaError_t prepare(K kern, KernelCache& c, int dev, int threads, int smem) {
-    if (c.ready_threads == threads) return cudaSuccess;
-    cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    if (err != cudaSuccess) return err;
-    int occ = 0;
+cudaError_t prepare(K kern, KernelCache& c, int dev, int threads, int smem, int smem_max, int* occ_out) {
+    const int w = threads / 32;
+    int occ = c.occ[w].load(std::memory_order_acquire);
+    if (occ > 0) { *occ_out = occ; return cudaSuccess; }
+    std::lock_guard<std::mutex> lk(c.mu);
+    cudaError_t err;
+    if (!c.attr_set) {
+        err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max);
+        if (err != cudaSuccess) return err;
+        err = cudaDeviceGetAttribute(&c.sms, cudaDevAttrMultiProcessorCount, dev);
+        if (err != cudaSuccess) return err;
+        cudaFuncAttributes fa;
+        err = cudaFuncGetAttributes(&fa, kern);
+        if (err != cudaSuccess) return err;
+        c.regs = fa.numRegs;
+        c.attr_set = true;
+    }
+    occ = 0;
     err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, threads, smem);
     if (err != cudaSuccess) return err;
     if (occ < 1) return cudaErrorLaunchOutOfResources;
-    int sms = 0;
-    err = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    if (err != cudaSuccess) return err;
-    cudaFuncAttributes fa;
-    err = cudaFuncGetAttributes(&fa, kern);
-    if (err != cudaSuccess) return err;
-    c.blocks_per_sm = occ; c.sms = sms; c.regs = fa.numRegs; c.ready_threads = threads;
+    c.occ[w].store(occ, std::memory_order_release);
+    *occ_out = occ;
     return cudaSuccess;
 }
 
+// The tensor map of the last TMA launch of this host thread: re-encoding costs a driver call per launch, and
+// sweeps / benches launch the same (pointer, batch) over and over.
+struct TmapCache {
+    void* A = nullptr; long long batch = -1; int n = 0, es = 0, mpw = 0, dev = -1;
+    CUtensorMap map;
+};
+template <typename T>
+inline cudaError_t cached_batch_tmap(const CUtensorMap** out, void* A, int n, long long batch, int mpw, int dev) {
+    static thread_local TmapCache c;
+    if (!(c.A == A && c.batch == batch && c.n == n && c.es == (int)sizeof(T) && c.mpw == mpw && c.dev == dev)) {
+        c.A = nullptr;
+        cudaError_t err = make_batch_tmap<T>(&c.map, A, n, batch, mpw);
+        if (err != cudaSuccess) return err;
+        c.A = A; c.batch = batch; c.n = n; c.es = (int)sizeof(T); c.mpw = mpw; c.dev = dev;
+    }
+    *out = &c.map;
+    return cudaSuccess;
+}
+
+// One launch of `kern` (persistent: at most one resident grid) with the geometry report the ABI exposes.
+// smem_of(warps) = dynamic shared memory for a block of that many warps; max_threads = what kern is compiled for.
+// `pre` runs after the one-time preparation and before the start event (tensor-map encode), `go` launches.
+struct LaunchCtx { long long batch; int threads; cudaStream_t stream; LaunchInfo* info; bool dry_run; cudaEvent_t ev0; int dev; };
+
+template <typename K, typename SmemOf, typename Go>
+cudaError_t run_kernel(K kern, KernelCache& c, const LaunchCtx& x, int max_threads, SmemOf smem_of, int mpw, int g,
+                       const char* name, Go go) {
+    if (x.threads > max_threads || x.threads < 32 || (x.threads % 32)) return cudaErrorInvalidConfiguration;
+    const int warps = x.threads / 32;
+    const int smem = smem_of(warps);
+    int occ = 0;
+    cudaError_t err = prepare(kern, c, x.dev, x.threads, smem, smem_of(max_threads / 32), &occ);
+    if (err != cudaSuccess) return err;
+    const long long ntiles = (x.batch + mpw - 1) / mpw;
+    long long blocks = (ntiles + warps - 1) / warps;
+    const long long resident = (long long)c.sms * occ;
+    if (blocks > resident) blocks = resident;  // persistent: every warp strides over tiles
+    if (x.info) {
+        x.info->threads_per_block = x.threads; x.info->threads_per_matrix = g; x.info->matrices_per_block = warps * mpw;
+        x.info->num_blocks = blocks; x.info->dyn_smem_bytes = smem; x.info->regs_per_thread = c.regs;
+        x.info->blocks_per_sm = occ; x.info->kernel = name;
+    }
+    if (x.dry_run || x.batch == 0) return cudaSuccess;
+    return go((unsigned)blocks, smem);
+}
+
 template <typename T, int N, int MODE>
-cudaError_t launch(void* A, int32_t* piv, long long batch, int threads, cudaStream_t stream,
-                   LaunchInfo* info, int flags) {
-    const int dry_run = flags & kLaunchDryRun;
-    if (threads <= 0) threads = 256;
-    const int warps = threads / 32;
+cudaError_t launch(void* A, int32_t* piv, long long batch, int threads_req, cudaStream_t stream,
+                   LaunchInfo* info, int flags, cudaEvent_t ev0) {
+    const bool dry_run = (flags & kLaunchDryRun) != 0;
     int dev = 0;
     cudaError_t err = cudaGetDevice(&dev);
     if (err != cudaSuccess) return err;
     if (dev < 0 || dev >= kMaxDevices) return cudaErrorInvalidDevice;
+    T* At = static_cast<T*>(A);
+    auto start = [&]() -> cudaError_t { return ev0 ? cudaEventRecord(ev0, stream) : cudaSuccess; };
+    LaunchCtx x{batch, threads_req > 0 ? threads_req : 256, stream, info, dry_run, ev0, dev};
 
     if (flags & kLaunchLuOnly) {  // factors only: the generic kernel's LU variant (not a tuned path)
         using AC = AutoCfg<T, N, MODE>;
         using GLU = Layout<T, N, AC::GR, AC::GC, MODE>;
-        static KernelCache cache_lu[kMaxDevices] = {};
+        static KernelCache cache_lu[kMaxDevices];
         auto kern = lub_invert_kernel<T, N, AC::GR, AC::GC, MODE, true>;
-        const int smem_lu = GLU::HEADER_BYTES + warps * GLU::WARP_BYTES;
-        KernelCache& cl = cache_lu[dev];
-        err = prepare(kern, cl, dev, threads, smem_lu);
-        if (err != cudaSuccess) return err;
-        const long long ntiles_lu = (batch + GLU::MPW - 1) / GLU::MPW;
-        long long blocks_lu = (ntiles_lu + warps - 1) / warps;
-        if (blocks_lu > (long long)cl.sms * cl.blocks_per_sm) blocks_lu = (long long)cl.sms * cl.blocks_per_sm;
-        if (info) {
-            info->threads_per_block = threads; info->threads_per_matrix = GLU::G; info->matrices_per_block = warps * GLU::MPW;
-            info->num_blocks = blocks_lu; info->dyn_smem_bytes = smem_lu; info->regs_per_thread = cl.regs;
-            info->blocks_per_sm = cl.blocks_per_sm; info->kernel = "lub_invert_kernel<LUONLY>";
-        }
-        if (dry_run || batch == 0) return cudaSuccess;
-        kern<<<(unsigned)blocks_lu, threads, smem_lu, stream>>>(static_cast<T*>(A), piv, batch);
-        return cudaGetLastError();
+        return run_kernel(kern, cache_lu[dev], x, kMaxThreads, [](int w) { return GLU::HEADER_BYTES + w * GLU::WARP_BYTES; }, GLU::MPW, GLU::G,
+                          "lub_invert_kernel<LUONLY>", [&](unsigned blocks, int smem) {
+                              cudaError_t e = start();
+                              if (e != cudaSuccess) return e;
+                              kern<<<blocks, x.threads, smem, stream>>>(At, piv, batch);
+                              return cudaGetLastError();
+                          });
     }
 
     using VC = V3Cfg<T, N, MODE>;
@@ -233,42 +306,49 @@ cudaError_t launch(void* A, int32_t* piv, long long batch, int threads, cudaStre
     // (profiles/r01_tune_f64.jsonl); fp32 and one-lane-per-matrix layouts stay on lub_v3.cuh
     constexpr bool USE_V4 = (sizeof(T) == 8) && (VC::GR * VC::GC > 1);
     using FL = typename std::conditional<USE_V4, V4Layout<T, N, VC::GR, VC::GC, MODE>, V3Layout<T, N, VC::GR, VC::GC, MODE>>::type;
-    using GL = Layout<T, N, AutoCfg<T, N, MODE>::GR, AutoCfg<T, N, MODE>::GC, MODE>;
-    // the fast kernel's vector accesses need a 16-byte aligned batch (cudaMalloc gives 256);
+    // the fast kernels' vector accesses need a 16-byte aligned batch (cudaMalloc gives 256);
     // anything else (a view starting mid-buffer at an odd element) takes the generic kernel
     const bool fast = dry_run || (reinterpret_cast<uintptr_t>(A) % 16 == 0);
+    static KernelCache cache_fast[kMaxDevices], cache_gen[kMaxDevices];
 
-    static KernelCache cache_fast[kMaxDevices] = {}, cache_gen[kMaxDevices] = {};
-    int smem, mpw, g;
-    KernelCache* c;
     using TC = TmaCfg<T, N, MODE>;
-    constexpr bool USE_TMA = TC::ON;
-    if constexpr (USE_TMA) {
-        if (fast) {
+    // TMA tile coordinates are 32-bit: larger batches take the v3 / v4 kernels (64-bit index arithmetic)
+    if constexpr (TC::ON) {
+        if (fast && batch <= 0x7fffff00ll) {
             using TL = TmaLayout<T, N, TC::GR, TC::GC, MODE>;
+            constexpr int NIMG = (TC::OPT & kTmaDB) ? 2 : 1;
             // no pivoting: results leave through the image and a bulk store (5-18 % faster than register
             // stores + in-place prefetch)
-            auto kern = lub_tma_kernel<T, N, TC::GR, TC::GC, MODE, VC::MINB, TC::BSYNC, false, MODE == kModeNone>;
-            smem = TL::smem_bytes(warps); mpw = TL::MPW; g = TL::G; c = &cache_fast[dev];
-            err = prepare(kern, *c, dev, threads, smem);
-            if (err != cudaSuccess) return err;
-            const long long ntiles = (batch + mpw - 1) / mpw;
-            long long blocks = (ntiles + warps - 1) / warps;
-            const long long resident = (long long)c->sms * c->blocks_per_sm;
-            if (blocks > resident) blocks = resident;
-            if (info) {
-                info->threads_per_block = threads; info->threads_per_matrix = g; info->matrices_per_block = warps * mpw;
-                info->num_blocks = blocks; info->dyn_smem_bytes = smem; info->regs_per_thread = c->regs;
-                info->blocks_per_sm = c->blocks_per_sm; info->kernel = "lub_tma_kernel";
-            }
-            if (dry_run || batch == 0) return cudaSuccess;
-            CUtensorMap map;
-            err = make_batch_tmap<T>(&map, A, N, batch, mpw);
-            if (err != cudaSuccess) return err;
-            kern<<<(unsigned)blocks, threads, smem, stream>>>(map, static_cast<T*>(A), piv, batch);
-            return cudaGetLastError();
+            auto kern = lub_tma_kernel<T, N, TC::GR, TC::GC, MODE, (TC::MAXT > kMaxThreads ? 1 : VC::MINB), TC::BSYNC, false, MODE == kModeNone,
+                                       false, TC::OPT, TC::MAXT>;
+            if (threads_req <= 0) x.threads = TC::THREADS;
+            return run_kernel(kern, cache_fast[dev], x, TC::MAXT, [](int w) { return TL::smem_bytes(w, NIMG); }, TL::MPW, TL::G, "lub_tma_kernel",
+                              [&](unsigned blocks, int smem) {
+                                  const CUtensorMap* map = nullptr;
+                                  cudaError_t e = cached_batch_tmap<T>(&map, A, N, batch, TL::MPW, dev);
+                                  if (e != cudaSuccess) return e;
+                                  e = start();
+                                  if (e != cudaSuccess) return e;
+                                  kern<<<blocks, x.threads, smem, stream>>>(*map, At, piv, batch);
+                                  return cudaGetLastError();
+                              });
         }
     }
+    if (!fast) {
+        using GL = Layout<T, N, AutoCfg<T, N, MODE>::GR, AutoCfg<T, N, MODE>::GC, MODE>;
+        auto kern = lub_invert_kernel<T, N, AutoCfg<T, N, MODE>::GR, AutoCfg<T, N, MODE>::GC, MODE>;
+        return run_kernel(kern, cache_gen[dev], x, kMaxThreads, [](int w) { return GL::HEADER_BYTES + w * GL::WARP_BYTES; }, GL::MPW, GL::G,
+                          "lub_invert_kernel", [&](unsigned blocks, int smem) {
+                              cudaError_t e = start();
+                              if (e != cudaSuccess) return e;
+                              kern<<<blocks, x.threads, smem, stream>>>(At, piv, batch);
+                              return cudaGetLastError();
+                          });
+    }
+    // When the TMA path is compiled in but not taken (batch beyond 32-bit tile coordinates) the fast cache entry
+    // would be shared by two kernels: keep a second one.
+    static KernelCache cache_fast2[kMaxDevices];
+    KernelCache& cf = TC::ON ? cache_fast2[dev] : cache_fast[dev];
     // no pivoting on the 16-byte image: the next tile is prefetched with cp.async while this one is
     // eliminated and the results leave straight from the registers (12-22 % faster, N = 16..24,
     // profiles/r01_tune_prefetch.jsonl); no per-tile block barrier there
@@ -276,65 +356,25 @@ cudaError_t launch(void* A, int32_t* piv, long long batch, int threads, cudaStre
     constexpr bool V3_PF = !USE_V4 && (MODE == kModeNone) && V3Layout<T, N, VC::GR, VC::GC, MODE>::ROWVEC && N >= 12;
     constexpr bool V3_PFD = !USE_V4 && pick_pfd(N, (int)sizeof(T), MODE);
     constexpr bool V4_PFD = USE_V4 && pick_pfd64(N, MODE);
-    if (fast) {
-        mpw = FL::MPW; g = FL::G; c = &cache_fast[dev];
-        if constexpr (V3_PFD) {
-            smem = FL::HEADER_BYTES + warps * FL::WARP_BYTES_PFD;
-            err = prepare(lub_v3_kernel<T, N, VC::GR, VC::GC, MODE, VC::MINB, VC::BSYNC, 0, false, true>, *c, dev, threads, smem);
-        } else if constexpr (USE_V4 && V4_PFD) {
-            smem = FL::HEADER_BYTES + warps * FL::WARP_BYTES_PFD;
-            err = prepare(lub_v4_kernel<T, N, VC::GR, VC::GC, MODE, VC::MINB, false, 0, true>, *c, dev, threads, smem);
-        } else if constexpr (USE_V4) {
-            smem = FL::HEADER_BYTES + warps * FL::WARP_BYTES;
-            err = prepare(lub_v4_kernel<T, N, VC::GR, VC::GC, MODE, VC::MINB, false, 0>, *c, dev, threads, smem);
-        } else if constexpr (V3_PF) {
-            smem = FL::HEADER_BYTES + warps * FL::WARP_BYTES_PF;
-            err = prepare(lub_v3_kernel<T, N, VC::GR, VC::GC, MODE, VC::MINB, false, 0, true>, *c, dev, threads, smem);
-        } else {
-            smem = FL::HEADER_BYTES + warps * FL::WARP_BYTES;
-            err = prepare(lub_v3_kernel<T, N, VC::GR, VC::GC, MODE, VC::MINB, VC::BSYNC>, *c, dev, threads, smem);
-        }
-    } else {
-        smem = GL::HEADER_BYTES + warps * GL::WARP_BYTES; mpw = GL::MPW; g = GL::G; c = &cache_gen[dev];
-        err = prepare(lub_invert_kernel<T, N, AutoCfg<T, N, MODE>::GR, AutoCfg<T, N, MODE>::GC, MODE>, *c, dev, threads, smem);
-    }
-    if (err != cudaSuccess) return err;
-
-    const long long ntiles = (batch + mpw - 1) / mpw;
-    long long blocks = (ntiles + warps - 1) / warps;
-    const long long resident = (long long)c->sms * c->blocks_per_sm;
-    if (blocks > resident) blocks = resident;  // persistent: every warp strides over tiles
-    if (info) {
-        info->threads_per_block = threads;
-        info->threads_per_matrix = g;
-        info->matrices_per_block = warps * mpw;
-        info->num_blocks = blocks;
-        info->dyn_smem_bytes = smem;
-        info->regs_per_thread = c->regs;
-        info->blocks_per_sm = c->blocks_per_sm;
-        info->kernel = !fast ? "lub_invert_kernel" : (USE_V4 ? "lub_v4_kernel" : "lub_v3_kernel");
-    }
-    if (dry_run || batch == 0) return cudaSuccess;
-    if (fast) {
-        if constexpr (V3_PFD)
-            lub_v3_kernel<T, N, VC::GR, VC::GC, MODE, VC::MINB, VC::BSYNC, 0, false, true>
-                <<<(unsigned)blocks, threads, smem, stream>>>(static_cast<T*>(A), piv, batch);
-        else if constexpr (USE_V4 && V4_PFD)
-            lub_v4_kernel<T, N, VC::GR, VC::GC, MODE, VC::MINB, false, 0, true>
-                <<<(unsigned)blocks, threads, smem, stream>>>(static_cast<T*>(A), piv, batch);
-        else if constexpr (USE_V4)
-            lub_v4_kernel<T, N, VC::GR, VC::GC, MODE, VC::MINB, false, 0>
-                <<<(unsigned)blocks, threads, smem, stream>>>(static_cast<T*>(A), piv, batch);
-        else if constexpr (V3_PF)
-            lub_v3_kernel<T, N, VC::GR, VC::GC, MODE, VC::MINB, false, 0, true>
-                <<<(unsigned)blocks, threads, smem, stream>>>(static_cast<T*>(A), piv, batch);
-        else
-            lub_v3_kernel<T, N, VC::GR, VC::GC, MODE, VC::MINB, VC::BSYNC>
-                <<<(unsigned)blocks, threads, smem, stream>>>(static_cast<T*>(A), piv, batch);
-    } else
-        lub_invert_kernel<T, N, AutoCfg<T, N, MODE>::GR, AutoCfg<T, N, MODE>::GC, MODE>
-            <<<(unsigned)blocks, threads, smem, stream>>>(static_cast<T*>(A), piv, batch);
-    return cudaGetLastError();
+    auto plain = [&](auto kern, int warp_bytes, const char* name) {
+        return run_kernel(kern, cf, x, kMaxThreads, [warp_bytes](int w) { return FL::HEADER_BYTES + w * warp_bytes; }, FL::MPW, FL::G, name,
+                          [&](unsigned blocks, int smem) {
+                              cudaError_t e = start();
+                              if (e != cudaSuccess) return e;
+                              kern<<<blocks, x.threads, smem, stream>>>(At, piv, batch);
+                              return cudaGetLastError();
+                          });
+    };
+    if constexpr (V3_PFD)
+        return plain(lub_v3_kernel<T, N, VC::GR, VC::GC, MODE, VC::MINB, VC::BSYNC, false, true>, FL::WARP_BYTES_PFD, "lub_v3_kernel");
+    else if constexpr (USE_V4 && V4_PFD)
+        return plain(lub_v4_kernel<T, N, VC::GR, VC::GC, MODE, VC::MINB, false, true>, FL::WARP_BYTES_PFD, "lub_v4_kernel");
+    else if constexpr (USE_V4)
+        return plain(lub_v4_kernel<T, N, VC::GR, VC::GC, MODE, VC::MINB, false>, FL::WARP_BYTES, "lub_v4_kernel");
+    else if constexpr (V3_PF)
+        return plain(lub_v3_kernel<T, N, VC::GR, VC::GC, MODE, VC::MINB, false, true>, FL::WARP_BYTES_PF, "lub_v3_kernel");
+    else
+        return plain(lub_v3_kernel<T, N, VC::GR, VC::GC, MODE, VC::MINB, VC::BSYNC>, FL::WARP_BYTES, "lub_v3_kernel");
 }
 
 // Each instantiation TU exports one of these for its (dtype, mode, N-range).

@@ -95,8 +95,8 @@ struct TmaLayout {
     static_assert(IMG_BYTES % 1024 == 0, "swizzle atoms are 1 KB");
     static constexpr int PERM_BYTES = (MODE != kModeNone) ? MPW * N * 4 : 0;
     static constexpr int HEADER_BYTES = 64;  // slot ranks of the reference tree (exact tie-break path)
-    static constexpr int smem_bytes(int warps) {  // + 1 KB slack to align the images by hand
-        return 1024 + warps * (IMG_BYTES + PERM_BYTES) + warps * 8 + HEADER_BYTES;
+    static constexpr int smem_bytes(int warps, int nimg = 1) {  // + 1 KB slack to align the images by hand
+        return 1024 + warps * (nimg * IMG_BYTES + PERM_BYTES) + warps * 16 + HEADER_BYTES;
     }
 };
 
@@ -320,13 +320,23 @@ __device__ __forceinline__ void st_global_256(double* p, const double* v) {
 // stores into the swizzled image, then one bulk tensor store -- instead of straight from the registers.
 // ST256 (register-store path only): 32-byte stores; needs a 32-byte aligned batch and an even number of
 // chunks per lane.
+// OPT (round 2): bit 0 = lean elimination step (gj_eliminate_lean); bit 1 = DB, two images per warp: the next
+// tile is requested right after the register load, into the image the previous tile left through (its bulk
+// store has long been read by then), so no warp waits on HBM for its input and the output image stays
+// untouched until its own bulk store has drained -- the pivot modes, whose column scatter needs the image
+// to the very end, get the prefetch that PF gives the no-pivot path.  MAXT = threads the kernel is compiled
+// for: 16 KB per warp means 12 warps per SM (one 384-thread block, up to 168 registers per thread).
+constexpr int kTmaLean = 1, kTmaDB = 2, kTmaFused = 4;
 template <typename T, int N, int GR, int GC, int MODE, int MINB = 2, bool BSYNC = true, bool PF = false, bool OUTIMG = false,
-          bool ST256 = false>
-__global__ void __launch_bounds__(kMaxThreads, MINB)
+          bool ST256 = false, int OPT = 0, int MAXT = kMaxThreads>
+__global__ void __launch_bounds__(MAXT, MINB)
 lub_tma_kernel(const __grid_constant__ CUtensorMap tmap, T* __restrict__ A, int32_t* __restrict__ piv, long long batch) {
     static_assert(!PF || MODE == kModeNone, "in-place prefetch: the pivot modes need the image for the column scatter");
     static_assert(!OUTIMG || (MODE == kModeNone && !PF), "OUTIMG is the no-pivot output path without in-place prefetch");
     constexpr bool VIA_IMG = (MODE != kModeNone) || OUTIMG;  // results go through the image and a bulk store
+    constexpr bool LEAN = (OPT & kTmaLean) != 0, DB = (OPT & kTmaDB) != 0;
+    static_assert(!DB || (VIA_IMG && !PF), "DB is the double-buffered form of the image-output path");
+    constexpr int NIMG = DB ? 2 : 1;
     using L = TmaLayout<T, N, GR, GC, MODE>;
     constexpr int G = L::G, MPW = L::MPW, LR = L::LR, LC = L::LC, CH = L::CH, CPL = L::CPL;
     constexpr int RB = L::RB, ES = L::ES;
@@ -337,14 +347,16 @@ lub_tma_kernel(const __grid_constant__ CUtensorMap tmap, T* __restrict__ A, int3
     const int nwarps = blockDim.x >> 5;
     // carve: [images, 1 KB aligned][perm][mbarriers][slot ranks]
     unsigned char* base = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);
-    unsigned char* img = base + (size_t)warp * L::IMG_BYTES;
-    unsigned char* after = base + (size_t)nwarps * L::IMG_BYTES;
+    unsigned char* img0 = base + (size_t)warp * (NIMG * L::IMG_BYTES);
+    unsigned char* img = img0;
+    unsigned char* after = base + (size_t)nwarps * (NIMG * L::IMG_BYTES);
     int* perm_all = reinterpret_cast<int*>(after + (size_t)warp * L::PERM_BYTES);
-    unsigned long long* bar = reinterpret_cast<unsigned long long*>(after + (size_t)nwarps * L::PERM_BYTES) + warp;
-    int8_t* slot_rank = reinterpret_cast<int8_t*>(after + (size_t)nwarps * L::PERM_BYTES + (size_t)nwarps * 8);
+    unsigned long long* bar0 = reinterpret_cast<unsigned long long*>(after + (size_t)nwarps * L::PERM_BYTES) + 2 * warp;
+    unsigned long long* bar = bar0;
+    int8_t* slot_rank = reinterpret_cast<int8_t*>(after + (size_t)nwarps * L::PERM_BYTES + (size_t)nwarps * 16);
 
     if (MODE == kModeParallel && threadIdx.x < N) slot_rank[threadIdx.x] = (int8_t)tree_slot_rank(threadIdx.x, N);
-    if (lane == 0) mbar_init(bar, 1);
+    if (lane == 0) { mbar_init(bar0, 1); mbar_init(bar0 + 1, 1); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     __syncthreads();
 
@@ -354,10 +366,11 @@ lub_tma_kernel(const __grid_constant__ CUtensorMap tmap, T* __restrict__ A, int3
     const int gc = g % GC;
     const int grp_base = ml * G;
     unsigned parity = 0;
+    unsigned iter = 0;  // DB: tiles this warp has started; image / barrier iter & 1, phase (iter >> 1) & 1
 
     const long long ntiles = (batch + MPW - 1) / MPW;
     const long long tstride = (long long)gridDim.x * nwarps;
-    if (PF && lane == 0) {
+    if ((PF || DB) && lane == 0) {
         const long long t0 = (long long)blockIdx.x * nwarps + warp;
         if (t0 < ntiles) {
             mbar_expect_tx(bar, (unsigned)L::IMG_BYTES);
@@ -374,7 +387,13 @@ lub_tma_kernel(const __grid_constant__ CUtensorMap tmap, T* __restrict__ A, int3
         T* gspan = A + first * (long long)(N * N);
 
         // ---- HBM -> swizzled image, by the TMA unit (matrices past the batch end read as zero) ----
-        if (!PF && lane == 0) {
+        if (DB) {
+            img = img0 + (iter & 1u) * L::IMG_BYTES;
+            bar = bar0 + (iter & 1u);
+            parity = (iter >> 1) & 1u;
+            ++iter;
+        }
+        if (!PF && !DB && lane == 0) {
             if (VIA_IMG) tma_store_wait_read();  // last round's tile has left the image
             mbar_expect_tx(bar, (unsigned)L::IMG_BYTES);
             tma_load_tile<L::LPR>(img, &tmap, bar, (int)first);
@@ -423,11 +442,20 @@ lub_tma_kernel(const __grid_constant__ CUtensorMap tmap, T* __restrict__ A, int3
                 tma_load_tile<L::LPR>(img, &tmap, bar, (int)(nxt * MPW));
             }
         }
+        if (DB) {  // the other image: last round's tile left it through a bulk store issued a whole search ago
+            const long long nxt = tile + tstride;
+            if (lane == 0 && nxt < ntiles) {
+                tma_store_wait_read();
+                mbar_expect_tx(bar0 + (iter & 1u), (unsigned)L::IMG_BYTES);
+                tma_load_tile<L::LPR>(img0 + (iter & 1u) * L::IMG_BYTES, &tmap, bar0 + (iter & 1u), (int)(nxt * MPW));
+            }
+        }
 
         T dinv[LR];
 #pragma unroll
         for (int li = 0; li < LR; ++li) dinv[li] = T(0);
-        gj_eliminate<T, N, GR, GC, CH, CPL, LR, LC>(a, dinv, gr, gc, grp_base);
+        if (LEAN) gj_eliminate_lean<T, N, GR, GC, CH, CPL, LR, LC>(a, dinv, gr, gc, grp_base);
+        else gj_eliminate<T, N, GR, GC, CH, CPL, LR, LC>(a, dinv, gr, gc, grp_base);
 
         // ---- scale by 1/pivot; undo the row permutation as a column scatter -------------------
 #pragma unroll

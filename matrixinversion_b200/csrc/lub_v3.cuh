@@ -208,18 +208,14 @@ __device__ __forceinline__ void copy_in_dense_async(unsigned char* __restrict__ 
     for (int b = head + nvec * 16 + lane * 4; b < bytes; b += 128) cp_async4(img + b, s + b);
 }
 
-// BSYNC: one block barrier per tile (see the loop).  DBG (tuning harness only): 1 = skip the
-// elimination, 2 = skip the pivot pre-pass (identity permutation), 4 = skip global loads/stores
-// after the first tile.  DBG is 0 in the product.
+// BSYNC: one block barrier per tile (see the loop).
 // In-register Gauss-Jordan on the LR x LC block of every lane: row k and column k travel by
 // shuffles, rows are scaled by 1/pivot only at the end (dinv), column k is overwritten with the
 // multipliers as it is cleared (in-place inverse).  Shared by lub_v3_kernel and lub_tma_kernel.
-// XDBG (tuning harness only, wrong results): 4 = no shuffles (lanes use their own registers),
-// 8 = no rank-1 update.
 // (Tried and dropped: doing the lane-dependent fix-ups with 0/1 masks on the FMA pipe instead of selects --
 // bit-identical results, but the compiler rebuilds the FFMA2 register pairs with extra MOVs and the
 // kernel gets 4 % slower, profiles/r01_tune_v6.md.)
-template <typename T, int N, int GR, int GC, int CH, int CPL, int LR, int LC, int XDBG = 0>
+template <typename T, int N, int GR, int GC, int CH, int CPL, int LR, int LC>
 __device__ __forceinline__ void gj_eliminate(T (&a)[LR][LC], T (&dinv)[LR], int gr, int gc, int grp_base) {
     constexpr int G = GR * GC;
 #pragma unroll
@@ -231,12 +227,12 @@ __device__ __forceinline__ void gj_eliminate(T (&a)[LR][LC], T (&dinv)[LR], int 
         T r[LC], c[LR];
 #pragma unroll
         for (int lj = 0; lj < LC; ++lj)
-            r[lj] = (GR > 1 && !(XDBG & 4)) ? shfl_t(a[lk][lj], grp_base + gro * GC + gc) : a[lk][lj];
+            r[lj] = (GR > 1) ? shfl_t(a[lk][lj], grp_base + gro * GC + gc) : a[lk][lj];
 #pragma unroll
         for (int li = 0; li < LR; ++li)
-            c[li] = (GC > 1 && !(XDBG & 4)) ? shfl_t(a[li][ck], grp_base + gr * GC + gco) : a[li][ck];
+            c[li] = (GC > 1) ? shfl_t(a[li][ck], grp_base + gr * GC + gco) : a[li][ck];
         // straight from the owner (not via r[ck]): all shuffles of a step leave in one batch
-        const T pv = (G > 1 && !(XDBG & 4)) ? shfl_t(a[lk][ck], grp_base + gro * GC + gco) : a[lk][ck];
+        const T pv = (G > 1) ? shfl_t(a[lk][ck], grp_base + gro * GC + gco) : a[lk][ck];
         const T rinv = rcp_t(pv);
         set_if(own_col, r[ck], T(1));
         T nf[LR];
@@ -247,12 +243,79 @@ __device__ __forceinline__ void gj_eliminate(T (&a)[LR][LC], T (&dinv)[LR], int 
 #pragma unroll
         for (int li = 0; li < LR; ++li) set_if(own_col, a[li][ck], (li == lk) ? diag : T(0));
 #pragma unroll
-        for (int li = 0; li < LR; ++li) {
-            if (!(XDBG & 8)) row_update<LC>(a[li], r, nf[li]);
-            else a[li][(li + k) % LC] += nf[li] * r[(li * 3 + k) % LC];  // keeps every value live
-        }
+        for (int li = 0; li < LR; ++li) row_update<LC>(a[li], r, nf[li]);
         set_if(own_row, dinv[lk], rinv);
     }
+}
+
+// ---- lean step (round 2) ----------------------------------------------------------------------
+// Same arithmetic as gj_eliminate, bit for bit, with the lane-dependent fix-ups re-planned around what
+// the B200 sub-partition actually charges (profiles/r02_issue_costs.md): an FSEL / MOV / predicated MOV
+// runs on the 16-lane ALU pipe (2 dispatch cycles) while a predicated FMUL runs on the FMA pipe (1 cycle);
+// and clearing column k BEFORE the rank-1 update overwrites a register the pending column shuffle still
+// reads, so the compiler renamed the pair and paid a MOV for the partner (8-9 MOVs per step).  Here
+//   * column k is not cleared at all: the owners of the column let the FFMA2 run over it and take their
+//     multiplier afterwards (a[li][ck] = nf[li]), an in-place write whose inputs have long arrived;
+//   * that copy, and the copy of 1/pivot into dinv, is a predicated multiplication by an opaque 1.0
+//     (a __constant__ the assembler cannot fold): FMA pipe, exact for every value;
+//   * r[ck] = 1 on the column owners is no longer needed (their column ck is overwritten anyway).
+// Per step and warp: 17 SHFL + 8 FMUL + 9 predicated FMUL + 2 predicated FFMA + 3 (reciprocal) besides the
+// 32 FFMA2, against 17 + 8 + ~11 FSEL + ~9 MOV + 3 before.  (The same fix-ups as in-place FSELs on the ALU pipe:
+// 2.52 ms against 2.33 ms on the headline, profiles/r02_tune_headline.jsonl -- the MOVs come back.)
+static __constant__ float kLubOne = 1.0f;
+static __constant__ float kLubZero = 0.0f;
+
+__device__ __forceinline__ void pset_fma(bool p, float& x, float v, float one) {
+    asm("{ .reg .pred q; setp.ne.s32 q, %1, 0; @q mul.rn.f32 %0, %2, %3; }" : "+f"(x) : "r"((int)p), "f"(v), "f"(one));
+}
+__device__ __forceinline__ void pset_fma(bool p, double& x, double v, double) { set_if(p, x, v); }
+// x = x * zero + c on the lanes where p holds (c = 0 or 1): a constant written by an FFMA that depends on x,
+// so the assembler cannot hoist it out of the step and turn the write back into an FSEL.  Exact for every
+// finite x; a non-finite x (zero pivot: the matrix is singular and the result inf/NaN as in the reference,
+// SURVEY Q7) stays non-finite.
+__device__ __forceinline__ void pconst_fma(bool p, float& x, float zero, float c) {
+    asm("{ .reg .pred q; setp.ne.s32 q, %1, 0; @q fma.rn.f32 %0, %0, %2, %3; }" : "+f"(x) : "r"((int)p), "f"(zero), "f"(c));
+}
+__device__ __forceinline__ void pconst_fma(bool p, double& x, double, double c) { set_if(p, x, c); }
+
+// One elimination step (pivot k); k is a compile-time constant after unrolling.
+template <typename T, int N, int GR, int GC, int CH, int CPL, int LR, int LC>
+__device__ __forceinline__ void gj_step_lean(T (&a)[LR][LC], T (&dinv)[LR], const int k, int gr, int gc, int grp_base, T one, T zero) {
+    constexpr int G = GR * GC;
+    const int gro = k % GR, lk = k / GR;
+    const int cj = k / CH, gco = cj / CPL, ck = (cj % CPL) * CH + (k % CH);
+    const bool own_row = (GR == 1) || (gr == gro);
+    const bool own_col = (GC == 1) || (gc == gco);
+    T r[LC], c[LR];
+#pragma unroll
+    for (int lj = 0; lj < LC; ++lj) r[lj] = (GR > 1) ? shfl_t(a[lk][lj], grp_base + gro * GC + gc) : a[lk][lj];
+#pragma unroll
+    for (int li = 0; li < LR; ++li) c[li] = (GC > 1) ? shfl_t(a[li][ck], grp_base + gr * GC + gco) : a[li][ck];
+    const T pv = (G > 1) ? shfl_t(a[lk][ck], grp_base + gro * GC + gco) : a[lk][ck];
+    const T rinv = rcp_t(pv);
+    T nf[LR];
+#pragma unroll
+    for (int li = 0; li < LR; ++li) nf[li] = -(c[li] * rinv);
+    if (GR == 1) nf[lk] = T(0);
+    else pconst_fma(own_row, nf[lk], zero, zero);
+#pragma unroll
+    for (int li = 0; li < LR; ++li) row_update<LC>(a[li], r, nf[li]);
+#pragma unroll
+    for (int li = 0; li < LR; ++li) {
+        if (GC == 1) a[li][ck] = nf[li];
+        else pset_fma(own_col, a[li][ck], nf[li], one);
+    }
+    if (G == 1) a[lk][ck] = T(1);
+    else pconst_fma(own_row && own_col, a[lk][ck], zero, one);
+    if (GR == 1) dinv[lk] = rinv;
+    else pset_fma(own_row, dinv[lk], rinv, one);
+}
+
+template <typename T, int N, int GR, int GC, int CH, int CPL, int LR, int LC>
+__device__ __forceinline__ void gj_eliminate_lean(T (&a)[LR][LC], T (&dinv)[LR], int gr, int gc, int grp_base) {
+    const T one = (T)kLubOne, zero = (T)kLubZero;
+#pragma unroll
+    for (int k = 0; k < N; ++k) gj_step_lean<T, N, GR, GC, CH, CPL, LR, LC>(a, dinv, k, gr, gc, grp_base, one, zero);
 }
 
 // PF (16-byte image layouts): the tile image is free again as soon as the registers are loaded, so
@@ -265,7 +328,7 @@ __device__ __forceinline__ void gj_eliminate(T (&a)[LR][LC], T (&dinv)[LR], int 
 // fetched with cp.async into the idle one while this tile is searched, eliminated and written back from
 // the other -- the pivot modes need their image until the very end (column scatter), so the in-place
 // prefetch of PF does not apply.
-template <typename T, int N, int GR, int GC, int MODE, int MINB = 1, bool BSYNC = true, int DBG = 0, bool PF = false, bool PFD = false>
+template <typename T, int N, int GR, int GC, int MODE, int MINB = 1, bool BSYNC = true, bool PF = false, bool PFD = false>
 __global__ void __launch_bounds__(kMaxThreads, MINB)
 lub_v3_kernel(T* __restrict__ A, int32_t* __restrict__ piv, long long batch) {
     using L = V3Layout<T, N, GR, GC, MODE>;
@@ -341,8 +404,6 @@ lub_v3_kernel(T* __restrict__ A, int32_t* __restrict__ piv, long long batch) {
             }
             cp_async_commit();
             cur ^= 1;
-        } else if ((DBG & 4) && tile >= (long long)gridDim.x * nwarps) {
-            img = reinterpret_cast<T*>(wbase);
         } else if constexpr (L::SC) {
             img = reinterpret_cast<T*>(wbase);
             copy_in_scatter<T, L, N>(img, gspan, nm * N * N, lane);
@@ -358,10 +419,7 @@ lub_v3_kernel(T* __restrict__ A, int32_t* __restrict__ piv, long long batch) {
 
         T* mimg = img + ml * MS;
         int* perm = perm_all + ml * N;
-        if ((DBG & 2) && MODE != kModeNone) {
-            for (int e = lane; e < MPW * N; e += 32) perm_all[e] = e % N;
-            __syncwarp();
-        } else if (MODE != kModeNone) {
+        if (MODE != kModeNone) {
             if (N > 16 || L::VECPIV) {
                 constexpr int MI = (MPW < 4) ? MPW : 4;
 #pragma unroll 1
@@ -410,14 +468,14 @@ lub_v3_kernel(T* __restrict__ A, int32_t* __restrict__ piv, long long batch) {
         T dinv[LR];
 #pragma unroll
         for (int li = 0; li < LR; ++li) dinv[li] = T(0);
-        if (!(DBG & 1)) gj_eliminate<T, N, GR, GC, CH, CPL, LR, LC>(a, dinv, gr, gc, grp_base);
+        gj_eliminate<T, N, GR, GC, CH, CPL, LR, LC>(a, dinv, gr, gc, grp_base);
 
         // ---- scale by 1/pivot, undo the row permutation as a column scatter -------------------
         __syncwarp();
 #pragma unroll
         for (int li = 0; li < LR; ++li) {
 #pragma unroll
-            for (int lj = 0; lj < LC; ++lj) a[li][lj] *= ((DBG & 1) ? T(1) : dinv[li]);
+            for (int lj = 0; lj < LC; ++lj) a[li][lj] *= dinv[li];
         }
         if constexpr (PF && MODE == kModeNone) {
             T* gm = gspan + (size_t)ml * (N * N);
@@ -484,7 +542,6 @@ lub_v3_kernel(T* __restrict__ A, int32_t* __restrict__ piv, long long batch) {
         }
         __syncwarp();
         if constexpr (PF) {
-        } else if ((DBG & 4) && tile >= (long long)gridDim.x * nwarps) {
         } else if constexpr (L::SC) copy_out_gather<T, L, N>(gspan, img, nm * N * N, lane);
         else if constexpr (L::ROWVEC) copy_out_padded<T, L, N>(gspan, wbase, nm * N * L::CPR16, lane);
         else copy_out<T>(gspan, img, nm * N * N, lane);

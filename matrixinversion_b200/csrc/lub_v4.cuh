@@ -116,16 +116,14 @@ __device__ __forceinline__ void row_update_masked(double (&a)[LC], const double 
     for (int j = 0; j < LC; ++j) a[j] = fma(nf, r[j], (j == cz) ? a[j] * zmask : a[j]);
 }
 
-// DBG bit 16 (tuning): fully unroll the inner steps as well
 // PFD (dense layouts): two images per warp, the next tile is fetched with cp.async into the idle one while
 // this tile is worked on (see lub_v3_kernel).
-template <typename T, int N, int GR, int GC, int MODE, int MINB = 1, bool BSYNC = true, int DBG = 0, bool PFD = false>
+template <typename T, int N, int GR, int GC, int MODE, int MINB = 1, bool BSYNC = true, bool PFD = false>
 __global__ void __launch_bounds__(kMaxThreads, MINB)
 lub_v4_kernel(T* __restrict__ A, int32_t* __restrict__ piv, long long batch) {
     using L = V4Layout<T, N, GR, GC, MODE>;
     static_assert(!PFD || L::DENSE, "double-buffered prefetch needs the dense image");
     constexpr int G = L::G, MPW = L::MPW, LR = L::LR, LC = L::LC, GM = L::GM, P = L::P, MS = L::MS;
-    constexpr unsigned STAGGER_NS = (DBG >> 8) * 500u;  // tuning: DBG bits 8.. = stagger quantum in 0.5 us
     extern __shared__ __align__(16) unsigned char smem_raw[];
 
     const int lane = threadIdx.x & 31;
@@ -149,13 +147,6 @@ lub_v4_kernel(T* __restrict__ A, int32_t* __restrict__ piv, long long batch) {
     const int grp_base = ml * G;
 
     const long long ntiles = (batch + MPW - 1) / MPW;
-    // De-phase the resident warps once: they all start a tile (a memory-bound staging phase
-    // followed by an FMA-bound elimination phase) at the same instant, and with equal work per
-    // tile they would stay in step, leaving HBM idle while every warp computes and vice versa.
-    if (STAGGER_NS > 0) {
-        const unsigned slot = BSYNC ? (blockIdx.x / 148u) % 4u : (unsigned)(warp + blockIdx.x) % 4u;
-        if (slot) __nanosleep(slot * STAGGER_NS);
-    }
     if constexpr (PFD) {
         const long long t0 = (long long)blockIdx.x * nwarps + warp;
         if (t0 < ntiles) {
@@ -190,18 +181,15 @@ lub_v4_kernel(T* __restrict__ A, int32_t* __restrict__ piv, long long batch) {
             cur ^= 1;
         } else if constexpr (L::DENSE) {  // the image is the span itself, shifted so that 16-byte chunks line up
             img = reinterpret_cast<T*>(wbase + (unsigned)(reinterpret_cast<uintptr_t>(gspan) & 15u));
-            if (!((DBG & 4) && tbase >= (long long)gridDim.x * nwarps)) copy_in<T>(img, gspan, nm * N * N, nm * N * N, lane);
+            copy_in<T>(img, gspan, nm * N * N, nm * N * N, lane);
         } else {
-            if (!((DBG & 4) && tbase >= (long long)gridDim.x * nwarps)) copy_in_scatter<T, L, N>(img, gspan, nm * N * N, lane);
+            copy_in_scatter<T, L, N>(img, gspan, nm * N * N, lane);
         }
         __syncwarp();
 
         T* mimg = img + ml * MS;
         int* perm = perm_all + ml * N;
-        if ((DBG & 2) && MODE != kModeNone) {
-            for (int e = lane; e < MPW * N; e += 32) perm_all[e] = e % N;
-            __syncwarp();
-        } else if (MODE != kModeNone) {
+        if (MODE != kModeNone) {
             if (N > 16) {
                 constexpr int MI = (MPW < 4) ? MPW : 4;
 #pragma unroll 1
@@ -233,14 +221,14 @@ lub_v4_kernel(T* __restrict__ A, int32_t* __restrict__ piv, long long batch) {
         T dinv[LR];
 #pragma unroll
         for (int li = 0; li < LR; ++li) dinv[li] = T(0);
-        constexpr int NSTEP = (DBG & 1) ? 0 : N;
+        constexpr int NSTEP = N;
 #pragma unroll
         for (int kb = 0; kb < (NSTEP + GM - 1) / GM; ++kb) {
             constexpr int dummy = 0; (void)dummy;
             const int lk = (kb * GM) / GR;          // local row of rows kb*GM .. kb*GM+GM-1
             const int ck = (kb * GM) / GC;          // local column of those columns
             const int gro0 = (kb * GM) % GR, gco0 = (kb * GM) % GC;
-#pragma unroll ((DBG & 16) ? GM : ((DBG & 32) ? 2 : 1))
+#pragma unroll 1
             for (int s = 0; s < GM; ++s) {
                 if (kb * GM + s >= NSTEP) break;
                 const int gro = gro0 + s, gco = gco0 + s;   // run-time owners of pivot row / column
@@ -264,15 +252,8 @@ lub_v4_kernel(T* __restrict__ A, int32_t* __restrict__ piv, long long batch) {
 #pragma unroll
                 for (int li = 0; li < LR; ++li) nf[li] = -(c[li] * rinv);
                 nf[lk] = sel_t(own_row, T(0), nf[lk]);
-                if (DBG & 64) {  // tuning: clear column k with selects (ALU pipe) and use the plain update
 #pragma unroll
-                    for (int li = 0; li < LR; ++li) a[li][ck] = sel_t(own_col, T(0), a[li][ck]);
-#pragma unroll
-                    for (int li = 0; li < LR; ++li) row_update<LC>(a[li], r, nf[li]);
-                } else {
-#pragma unroll
-                    for (int li = 0; li < LR; ++li) row_update_masked<LC>(a[li], r, nf[li], ck, zmask);
-                }
+                for (int li = 0; li < LR; ++li) row_update_masked<LC>(a[li], r, nf[li], ck, zmask);
                 // the pivot row's own slot-k entry is the 1 of the identity column
                 a[lk][ck] = sel_t(own_row && own_col, T(1), a[lk][ck]);
                 dinv[lk] = sel_t(own_row, rinv, dinv[lk]);
@@ -292,16 +273,16 @@ lub_v4_kernel(T* __restrict__ A, int32_t* __restrict__ piv, long long batch) {
         for (int li = 0; li < LR; ++li) {
             const int i = li * GR + gr;
             const bool rok = (li * GR + GR - 1 < N) || (i < N);
-            const T sc = (DBG & 1) ? T(1) : dinv[li];
+            const T sc = dinv[li];
 #pragma unroll
             for (int lj = 0; lj < LC; ++lj)
                 if (rok && pcol[lj] >= 0) mimg[i * P + pcol[lj]] = a[li][lj] * sc;
         }
         __syncwarp();
         if constexpr (L::DENSE) {
-            if (!((DBG & 4) && tbase >= (long long)gridDim.x * nwarps)) copy_out<T>(gspan, img, nm * N * N, lane);
+            copy_out<T>(gspan, img, nm * N * N, lane);
         } else {
-            if (!((DBG & 4) && tbase >= (long long)gridDim.x * nwarps)) copy_out_gather<T, L, N>(gspan, img, nm * N * N, lane);
+            copy_out_gather<T, L, N>(gspan, img, nm * N * N, lane);
         }
         int32_t* pivp = piv;
         asm volatile("" : "+l"(pivp));  // opaque: keeps the compiler from cloning the whole tile loop on piv == NULL

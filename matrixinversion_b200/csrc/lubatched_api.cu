@@ -43,8 +43,9 @@ thread_local std::string g_err;
 thread_local cudaStream_t g_stream = nullptr;
 thread_local int g_threads = 0;
 thread_local bool g_timing = false;
-thread_local cudaEvent_t g_ev0 = nullptr, g_ev1 = nullptr;
-thread_local bool g_ev_valid = false;
+// start / stop events of the timed launch, one pair per device (events belong to the device they were created on)
+thread_local cudaEvent_t g_ev[lub::kMaxDevices][2] = {};
+thread_local int g_ev_dev = -1;  // device of the last timed launch, -1 = none
 
 int fail(int code, const std::string& msg) {
     g_err = msg;
@@ -79,13 +80,18 @@ int launch_on(void* ptr, int32_t* piv, int n, int64_t batch, int mode, int dtype
     lub::LaunchFn fn = lub::find_launcher(n, mode, dtype);
     if (!fn) return fail(LUB_ERR_BAD_N, "no kernel for this n");
     const bool timed = g_timing && !dry && batch > 0;
+    int dev = 0;
     if (timed) {
-        if (!g_ev0) { CU(cudaEventCreate(&g_ev0)); CU(cudaEventCreate(&g_ev1)); }
-        CU(cudaEventRecord(g_ev0, s));
+        CU(cudaGetDevice(&dev));
+        if (dev < 0 || dev >= lub::kMaxDevices) return fail(LUB_ERR_CUDA, "device index out of range");
+        if (!g_ev[dev][0]) { CU(cudaEventCreate(&g_ev[dev][0])); CU(cudaEventCreate(&g_ev[dev][1])); }
+        g_ev_dev = -1;
     }
-    cudaError_t e = fn(ptr, piv, (long long)batch, g_threads, s, info, flags);
+    // the launcher records the start event itself, after its one-time preparation (function attributes,
+    // occupancy query, tensor-map encode): the interval is the kernel's, also on the first call
+    cudaError_t e = fn(ptr, piv, (long long)batch, g_threads, s, info, flags, timed ? g_ev[dev][0] : nullptr);
     if (e != cudaSuccess) return cuda_fail(e, "kernel launch");
-    if (timed) { CU(cudaEventRecord(g_ev1, s)); g_ev_valid = true; }
+    if (timed) { CU(cudaEventRecord(g_ev[dev][1], s)); g_ev_dev = dev; }
     return LUB_OK;
 }
 
@@ -231,21 +237,25 @@ int lu_batched_set_threads(int numthreads) {
 }
 
 int lu_batched_get_threads(int n, int dtype) {
-    (void)n; (void)dtype;
-    return g_threads ? g_threads : 256;
+    if (g_threads) return g_threads;
+    // the library's own default for this size and type (pivot_mode parallel, the reference's headline variant);
+    // needs a device, like lu_batched_geometry
+    lub::LaunchInfo info{};
+    if (launch_on(nullptr, nullptr, n, 1, LUB_PIVOT_PARALLEL, dtype, nullptr, &info, lub::kLaunchDryRun) != LUB_OK) return -1;
+    return info.threads_per_block;
 }
 
 int lu_batched_enable_timing(int on) {
     g_timing = on != 0;
-    g_ev_valid = false;
+    g_ev_dev = -1;
     return LUB_OK;
 }
 
 float lu_batched_last_kernel_ms(void) {
-    if (!g_ev_valid) return -1.f;
-    if (cudaEventSynchronize(g_ev1) != cudaSuccess) return -1.f;
+    if (g_ev_dev < 0) return -1.f;
+    if (cudaEventSynchronize(g_ev[g_ev_dev][1]) != cudaSuccess) return -1.f;
     float ms = -1.f;
-    if (cudaEventElapsedTime(&ms, g_ev0, g_ev1) != cudaSuccess) return -1.f;
+    if (cudaEventElapsedTime(&ms, g_ev[g_ev_dev][0], g_ev[g_ev_dev][1]) != cudaSuccess) return -1.f;
     return ms;
 }
 
@@ -328,7 +338,10 @@ int lu_batched_inplace_host(void* host_ptr, int32_t* host_piv, int n, int64_t ba
         cudaStream_t s = P.st[slot];
         CU(cudaMemcpyAsync(P.buf[slot], h + (size_t)b0 * mat_bytes, (size_t)nb * mat_bytes, cudaMemcpyHostToDevice, s));
         rc = launch_on(P.buf[slot], host_piv ? P.pbuf[slot] : nullptr, n, nb, pivot_mode, dtype, s, nullptr, 0);
-        if (rc != LUB_OK) return rc;
+        if (rc != LUB_OK) {  // copies already queued still read / write the caller's buffer: drain them first
+            for (int i = 0; i < HostPipe::kSlots; ++i) cudaStreamSynchronize(P.st[i]);
+            return rc;
+        }
         CU(cudaMemcpyAsync(h + (size_t)b0 * mat_bytes, P.buf[slot], (size_t)nb * mat_bytes, cudaMemcpyDeviceToHost, s));
         if (host_piv) CU(cudaMemcpyAsync(host_piv + b0 * n, P.pbuf[slot], (size_t)nb * n * 4, cudaMemcpyDeviceToHost, s));
     }
@@ -346,33 +359,51 @@ int lu_batched_verify_inv(const void* A, const void* Ainv, int n, int64_t batch,
     return LUB_OK;
 }
 
-int lu_batched_verify_inv_device(const void* dA, const void* dAinv, int n, int64_t batch, int dtype, double thr,
-                                 int64_t* n_correct, int64_t* n_incorrect, double* max_abs_dev) {
+namespace {
+// device-side accumulator of lu_batched_verify_inv_device: one small allocation per (host thread, device), kept
+struct VerifyAcc { unsigned long long good; unsigned int worst; unsigned int nan; };
+thread_local VerifyAcc* g_vacc[lub::kMaxDevices] = {};
+
+int verify_inv_device_on(const void* dA, const void* dAinv, int n, int64_t batch, int dtype, double thr, int64_t* n_correct,
+                         int64_t* n_incorrect, double* max_abs_dev, cudaStream_t stream) {
     if (n < 1 || n > 1024) return fail(LUB_ERR_BAD_N, "n out of range");
     if (dtype != LUB_DTYPE_F32 && dtype != LUB_DTYPE_F64) return fail(LUB_ERR_BAD_DTYPE, "dtype must be 0 or 1");
     if (batch < 0 || (!dA && batch) || (!dAinv && batch)) return fail(LUB_ERR_BAD_ARG, "bad buffers");
-    struct Acc { unsigned long long good; unsigned int worst; unsigned int nan; };
-    Acc* d = nullptr;
-    CU(cudaMalloc((void**)&d, sizeof(Acc)));
-    CU(cudaMemsetAsync(d, 0, sizeof(Acc), g_stream));
+    int dev = 0, sms = 0;
+    CU(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= lub::kMaxDevices) return fail(LUB_ERR_CUDA, "device index out of range");
+    CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    if (!g_vacc[dev]) CU(cudaMalloc((void**)&g_vacc[dev], sizeof(VerifyAcc)));
+    VerifyAcc* d = g_vacc[dev];
+    CU(cudaMemsetAsync(d, 0, sizeof(VerifyAcc), stream));
     if (batch > 0) {
         const int threads = 256;
         const long long want = (batch * 32 + threads - 1) / threads;
-        const unsigned blocks = (unsigned)std::min<long long>(want, 148ll * 16);
+        const unsigned blocks = (unsigned)std::min<long long>(want, (long long)sms * 16);
         if (dtype == LUB_DTYPE_F32)
-            verify_kernel<float><<<blocks, threads, 0, g_stream>>>(static_cast<const float*>(dA), static_cast<const float*>(dAinv), n, batch, (float)thr, &d->good, &d->worst, &d->nan);
+            verify_kernel<float><<<blocks, threads, 0, stream>>>(static_cast<const float*>(dA), static_cast<const float*>(dAinv), n, batch, (float)thr, &d->good, &d->worst, &d->nan);
         else
-            verify_kernel<double><<<blocks, threads, 0, g_stream>>>(static_cast<const double*>(dA), static_cast<const double*>(dAinv), n, batch, thr, &d->good, &d->worst, &d->nan);
+            verify_kernel<double><<<blocks, threads, 0, stream>>>(static_cast<const double*>(dA), static_cast<const double*>(dAinv), n, batch, thr, &d->good, &d->worst, &d->nan);
         CU(cudaGetLastError());
     }
-    Acc h{};
-    CU(cudaMemcpyAsync(&h, d, sizeof(Acc), cudaMemcpyDeviceToHost, g_stream));
-    CU(cudaStreamSynchronize(g_stream));
-    cudaFree(d);
+    VerifyAcc h{};
+    CU(cudaMemcpyAsync(&h, d, sizeof(VerifyAcc), cudaMemcpyDeviceToHost, stream));
+    CU(cudaStreamSynchronize(stream));
     if (n_correct) *n_correct = (int64_t)h.good;
     if (n_incorrect) *n_incorrect = batch - (int64_t)h.good;
     if (max_abs_dev) { float w; memcpy(&w, &h.worst, 4); *max_abs_dev = h.nan ? NAN : (double)w; }
     return LUB_OK;
+}
+}  // namespace
+
+int lu_batched_verify_inv_device(const void* dA, const void* dAinv, int n, int64_t batch, int dtype, double thr,
+                                 int64_t* n_correct, int64_t* n_incorrect, double* max_abs_dev) {
+    return verify_inv_device_on(dA, dAinv, n, batch, dtype, thr, n_correct, n_incorrect, max_abs_dev, g_stream);
+}
+
+int lu_batched_verify_inv_device_stream(const void* dA, const void* dAinv, int n, int64_t batch, int dtype, double thr,
+                                        int64_t* n_correct, int64_t* n_incorrect, double* max_abs_dev, void* stream) {
+    return verify_inv_device_on(dA, dAinv, n, batch, dtype, thr, n_correct, n_incorrect, max_abs_dev, static_cast<cudaStream_t>(stream));
 }
 
 int lu_batched_read_tokens(const char* path, void* out, int64_t count, int dtype) {

@@ -15,7 +15,7 @@
 //   * slots form a ring guarded by two mbarriers each (full / empty), tiles are dealt round-robin,
 //     so there is no queue, no atomics and no block barrier after start-up.
 #pragma once
-#include "lub_v4.cuh"
+#include "../../matrixinversion_b200/csrc/lub_v4.cuh"
 
 namespace lub {
 

@@ -19,7 +19,7 @@
 // multiple of both warp counts, so every slot keeps its producer and consumer and the hand-over is a
 // pair of mbarriers per slot (hardware-suspended waits, no polling).
 #pragma once
-#include "lub_tma.cuh"
+#include "../../matrixinversion_b200/csrc/lub_tma.cuh"
 
 namespace lub {
 

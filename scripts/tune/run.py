@@ -55,6 +55,9 @@ for i in range(T.tune_count()):
                 close = bool(torch.allclose(A, ref, rtol=1e-3, atol=1e-3, equal_nan=True))
             else:
                 best = min(best, e0.elapsed_time(e1))
+        if not ok:
+            print(json.dumps({"variant": name, "threads": threads, "ok": False}), flush=True)
+            continue
         es = 4 if tdt == torch.float32 else 8
         print(json.dumps({"variant": name, "threads": threads, "ok": ok, "ms": round(best, 4), "occ_blocks": occ.value,
                           "GBps": round(2 * n * n * es * a.batch / best / 1e6), "piv_equal": same, "values_close": close}), flush=True)

@@ -2,9 +2,9 @@
 // fast kernel for a handful of lane layouts, launched by index so that scripts/tune/run.py can
 // time them side by side on the GPU box.  Build: make -C scripts/tune
 #include <cstdio>
-#include "../../matrixinversion_b200/csrc/lub_v5.cuh"
-#include "../../matrixinversion_b200/csrc/lub_tma.cuh"
-#include "../../matrixinversion_b200/csrc/lub_v6.cuh"
+#include "lub_v5.cuh"
+#include "lub_tma2.cuh"
+#include "lub_v6.cuh"
 
 using namespace lub;
 
@@ -21,14 +21,14 @@ template <typename T, int N, int GR, int GC, int MODE, int MINB, int DBG = 0>
 struct V3 {
     using L = V3Layout<T, N, GR, GC, MODE>;
     static void set_attr(int smem) {
-        cudaFuncSetAttribute(lub_v3_kernel<T, N, GR, GC, MODE, MINB, (DBG & 8) != 0, (DBG & 7), (DBG & 16) != 0, (DBG & 32) != 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        cudaFuncSetAttribute(lub_v3_kernel<T, N, GR, GC, MODE, MINB, (DBG & 8) != 0, (DBG & 16) != 0, (DBG & 32) != 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     }
     static void launch(void* A, int* piv, long long batch, unsigned blocks, int threads, int smem, cudaStream_t s) {
-        lub_v3_kernel<T, N, GR, GC, MODE, MINB, (DBG & 8) != 0, (DBG & 7), (DBG & 16) != 0, (DBG & 32) != 0><<<blocks, threads, smem, s>>>((T*)A, piv, batch);
+        lub_v3_kernel<T, N, GR, GC, MODE, MINB, (DBG & 8) != 0, (DBG & 16) != 0, (DBG & 32) != 0><<<blocks, threads, smem, s>>>((T*)A, piv, batch);
     }
     static int occ(int threads, int smem) {
         int o = 0;
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, lub_v3_kernel<T, N, GR, GC, MODE, MINB, (DBG & 8) != 0, (DBG & 7), (DBG & 16) != 0, (DBG & 32) != 0>, threads, smem);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, lub_v3_kernel<T, N, GR, GC, MODE, MINB, (DBG & 8) != 0, (DBG & 16) != 0, (DBG & 32) != 0>, threads, smem);
         return o;
     }
     static Variant make(const char* name) { return Variant{name, L::MPW, (DBG & 16) ? L::WARP_BYTES_PF : ((DBG & 32) ? L::WARP_BYTES_PFD : L::WARP_BYTES), L::HEADER_BYTES, set_attr, launch, occ}; }
@@ -38,14 +38,14 @@ template <typename T, int N, int GR, int GC, int MODE, int MINB, int DBG = 0>
 struct V {
     using L = V4Layout<T, N, GR, GC, MODE>;
     static void set_attr(int smem) {
-        cudaFuncSetAttribute(lub_v4_kernel<T, N, GR, GC, MODE, MINB, (DBG & 8) != 0, (DBG & ~(8 | 32)), (DBG & 32) != 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        cudaFuncSetAttribute(lub_v4_kernel<T, N, GR, GC, MODE, MINB, (DBG & 8) != 0, (DBG & 32) != 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     }
     static void launch(void* A, int* piv, long long batch, unsigned blocks, int threads, int smem, cudaStream_t s) {
-        lub_v4_kernel<T, N, GR, GC, MODE, MINB, (DBG & 8) != 0, (DBG & ~(8 | 32)), (DBG & 32) != 0><<<blocks, threads, smem, s>>>((T*)A, piv, batch);
+        lub_v4_kernel<T, N, GR, GC, MODE, MINB, (DBG & 8) != 0, (DBG & 32) != 0><<<blocks, threads, smem, s>>>((T*)A, piv, batch);
     }
     static int occ(int threads, int smem) {
         int o = 0;
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, lub_v4_kernel<T, N, GR, GC, MODE, MINB, (DBG & 8) != 0, (DBG & ~(8 | 32)), (DBG & 32) != 0>, threads, smem);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, lub_v4_kernel<T, N, GR, GC, MODE, MINB, (DBG & 8) != 0, (DBG & 32) != 0>, threads, smem);
         return o;
     }
     static Variant make(const char* name) { return Variant{name, L::MPW, (DBG & 32) ? L::WARP_BYTES_PFD : L::WARP_BYTES, L::HEADER_BYTES, set_attr, launch, occ}; }
@@ -69,11 +69,13 @@ struct V5 {
 };
 
 // TMA-staged kernel: warp_bytes == -1000000 marks it; launch builds the tensor map per call
-template <typename T, int N, int GR, int GC, int MODE, int MINB, int BS>
+// BS: bit 0 = BSYNC, 1 = PF, 2 = OUTIMG, 3 = ST256, 4 = lean step, 5 = double-buffered image, 6 = pivot search of the next tile fused into the elimination; MAXT = compiled block size
+template <typename T, int N, int GR, int GC, int MODE, int MINB, int BS, int MAXT = 256>
 struct VT {
     using L = TmaLayout<T, N, GR, GC, MODE>;
     static constexpr bool PF = (BS & 2) != 0;
-    static constexpr auto kern() { return lub_tma_kernel<T, N, GR, GC, MODE, MINB, (BS & 1) != 0, PF, (BS & 4) != 0, (BS & 8) != 0>; }
+    static constexpr int OPT = ((BS & 16) ? kTmaLean : 0) | ((BS & 32) ? kTmaDB : 0) | ((BS & 64) ? kTmaFused : 0);
+    static constexpr auto kern() { return lub_tma_kernel<T, N, GR, GC, MODE, MINB, (BS & 1) != 0, PF, (BS & 4) != 0, (BS & 8) != 0, OPT, MAXT>; }
     static void set_attr(int smem) { cudaFuncSetAttribute(kern(), cudaFuncAttributeMaxDynamicSharedMemorySize, smem); }
     static void launch(void* A, int* piv, long long batch, unsigned blocks, int threads, int smem, cudaStream_t s) {
         CUtensorMap map;
@@ -85,9 +87,32 @@ struct VT {
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, kern(), threads, smem);
         return o;
     }
-    static Variant make(const char* name) { return Variant{name, L::MPW, -1000000, 0, set_attr, launch, occ, &L::smem_bytes}; }
+    static int smem_of(int warps) { return L::smem_bytes(warps, (BS & 32) ? 2 : 1); }
+    static Variant make(const char* name) { return Variant{name, L::MPW, -1000000, MAXT, set_attr, launch, occ, &smem_of}; }
 };
 #define VART(T, N, GR, GC, MODE, MINB, BS) VT<T, N, GR, GC, MODE, MINB, BS>::make(#T " N=" #N " " #GR "x" #GC " mode" #MODE " minb" #MINB " bs" #BS " tma")
+#define VARTM(T, N, GR, GC, MODE, MINB, BS, MAXT) VT<T, N, GR, GC, MODE, MINB, BS, MAXT>::make(#T " N=" #N " " #GR "x" #GC " mode" #MODE " minb" #MINB " bs" #BS " maxt" #MAXT " tma")
+
+// round-2 fused kernel (lub_tma2.cuh): double-buffered image, next tile's pivot search inside the elimination
+template <int N, int GR, int GC, int MODE, int MAXT, int K1>
+struct VT2 {
+    using L = Tma2Layout<N, GR, GC, MODE>;
+    static constexpr auto kern() { return lub_tma2_kernel<N, GR, GC, MODE, MAXT, K1>; }
+    static void set_attr(int smem) { cudaFuncSetAttribute(kern(), cudaFuncAttributeMaxDynamicSharedMemorySize, smem); }
+    static void launch(void* A, int* piv, long long batch, unsigned blocks, int threads, int smem, cudaStream_t s) {
+        CUtensorMap map;
+        if (make_batch_tmap<float>(&map, A, N, batch, L::MPW) != cudaSuccess) { printf("tensor map failed\n"); return; }
+        kern()<<<blocks, threads, smem, s>>>(map, (float*)A, piv, batch);
+    }
+    static int occ(int threads, int smem) {
+        int o = 0;
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, kern(), threads, smem);
+        return o;
+    }
+    static int smem_of(int warps) { return L::smem_bytes(warps); }
+    static Variant make(const char* name) { return Variant{name, L::MPW, -1000000, MAXT, set_attr, launch, occ, &smem_of}; }
+};
+#define VART2(N, GR, GC, MODE, MAXT, K1) VT2<N, GR, GC, MODE, MAXT, K1>::make("float N=" #N " " #GR "x" #GC " mode" #MODE " maxt" #MAXT " k1_" #K1 " tma2")
 
 // warp-specialised TMA kernel: one persistent block per SM; warp_bytes == -2000000 marks it
 template <typename T, int N, int GR, int GC, int MODE, int NCW, int NPW, int NB, int CREG, int PREG, int NCG, int LA, int DBG>
@@ -124,6 +149,7 @@ extern "C" const char* tune_name(int i) { return variants[i].name; }
 extern "C" int tune_launch(int i, void* A, int* piv, long long batch, int threads, void* stream, int* occ_out, int* blocks_out) {
     Variant& v = variants[i];
     if (v.smem_of) {
+        if (threads > v.header) return -3;  // compiled for at most v.header threads per block
         const int warps = threads / 32;
         const int smem = v.smem_of(warps);
         v.set_attr(smem);

@@ -4,11 +4,18 @@ sm_100 (oracle/_ref, built in the container from /root/reference) are the checke
 
 Tolerances (north star):
   * pivots / permutation vectors: bit-exact;
-  * inverses: ||A X - I||_F <= C_RES * N * eps * kappa_2(A)   (residual in fp64, kappa from
-    numpy in fp64 -- never the reference's calc_cond_num), and elementwise
-    max|X - X_ref| <= C_ELEM * N * eps * kappa_2(A) * max|X_ref| against the oracle and
-    against the reference GPU kernels.
+  * inverses: ||A X - I||_F <= C_RES * N * eps * kappa_2(A) with C_RES = 64 (residual
+    in fp64, kappa from numpy in fp64 -- never the reference's calc_cond_num), or -- where
+    the reference's own pivot rule (arg-max over un-eliminated entries, Q1) lets elements grow and the
+    reference algorithm itself misses that bound -- at most 4x the residual of the checker's result for the
+    same matrix; and elementwise max|X - X_ref| <= C_ELEM * N * eps * kappa_2(A) * max|A^-1| (or 4x the
+    checker's own distance from the float64 LAPACK inverse) against the oracle and the reference GPU kernels.
+  Every check records the constant it actually needed; the session writes the per-(N, mode, dtype) table
+  to gpurun_out/parity_constants.json (committed copy: profiles/r02_parity_constants.json).
 """
+import atexit
+import json
+import os
 import io
 
 import numpy as np
@@ -21,8 +28,31 @@ from oracle import oracle as O
 torch = pytest.importorskip("torch")
 pytestmark = pytest.mark.gpu
 
-C_RES = 128.0    # the "stated constant c": oracle worst case is 36, Gauss-Jordan about 2x that
+C_RES = 64.0     # the "stated constant c" of the north star
 C_ELEM = 16.0
+HATCH = 4.0      # ... or this many times the checker's own error on the same matrix
+
+_CONST = {}      # (n, mode, dtype) -> [matrices, worst c with rho = 1, matrices above C_RES (needed the hatch)]
+
+
+def _record(n, mode, dtype, c, over):
+    e = _CONST.setdefault("n=%d mode=%d %s" % (n, mode, np.dtype(dtype).name), [0, 0.0, 0])
+    e[0] += int(c.size)
+    e[1] = max(e[1], float(c.max()) if c.size else 0.0)
+    e[2] += int(over)
+
+
+@atexit.register
+def _dump_constants():
+    if not _CONST:
+        return
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    os.makedirs(os.path.join(root, "gpurun_out"), exist_ok=True)
+    rows = {k: {"matrices": v[0], "worst_c": round(v[1], 3), "above_c_res": v[2]} for k, v in sorted(_CONST.items())}
+    worst = max(v[1] for v in _CONST.values())
+    with open(os.path.join(root, "gpurun_out", "parity_constants.json"), "w") as f:
+        json.dump({"c_res": C_RES, "hatch": HATCH, "worst_c_overall": worst,
+                   "cells_above_c_res": sum(1 for v in _CONST.values() if v[2]), "cells": rows}, f, indent=1)
 EPS = {np.dtype(np.float32): 2.0 ** -23, np.dtype(np.float64): 2.0 ** -52}
 MODES = (0, 1, 2)
 
@@ -36,47 +66,35 @@ def gpu_invert(A, mode, want_piv=True):
     return dA.cpu().numpy(), (piv.cpu().numpy() if want_piv else None)
 
 
-def growth(A, mode):
-    """rho = || |L||U| ||_inf / ||A||_inf of the reference's factorisation of every matrix (the
-    quantity that bounds the backward error of Gaussian elimination for a GIVEN pivot
-    sequence, Higham ASNA Thm 9.3).  1 for a stable sequence; the reference's rule -- arg-max
-    over un-eliminated entries, SURVEY.md Q1 -- does not bound it."""
-    with np.errstate(all="ignore"):
-        LU, _ = O.lu_batched(A.astype(np.float64), mode, lu_only=True)
-    Lm = np.tril(LU, -1) + np.eye(A.shape[1])
-    Um = np.triu(LU)
-    num = np.abs(np.abs(Lm) @ np.abs(Um)).sum(axis=2).max(axis=1)
-    den = np.abs(A.astype(np.float64)).sum(axis=2).max(axis=1)
-    rho = num / den
-    return np.where(np.isfinite(rho), np.maximum(rho, 1.0), np.inf)
-
-
 def check_values(A, X, Xref, what, mode=0):
     """Residual + elementwise bounds for every matrix of a (small) batch:
 
-        ||A X - I||_F            <= C_RES  * N * eps * kappa_2(A) * rho
-        max|X - Xref| / max|A^-1| <= C_ELEM * N * eps * kappa_2(A) * rho
+        ||A X - I||_F             <= max(C_RES  * N * eps * kappa_2(A), HATCH * ||A Xref - I||_F)
+        max|X - Xref| / max|A^-1| <= max(C_ELEM * N * eps * kappa_2(A), HATCH * max|Xref - A^-1| / max|A^-1|)
 
-    rho = 1 is the north star's bound; rho (see growth()) is > 1 only where the reference's
-    own pivot sequence lets elements grow, in which case the reference's result is off by the
-    same factor (checked: we also accept 8x the reference's own error measured against a
-    float64 LAPACK inverse)."""
+    The first term is the north star's bound.  The second only matters where the reference's pivot sequence
+    lets elements grow (SURVEY.md Q1) so that the reference algorithm itself is off by more than the bound;
+    how often it was needed is recorded (see _record)."""
+    if A.shape[0] == 0:
+        return
     eps = EPS[A.dtype]
     n = A.shape[1]
     A64 = A.astype(np.float64)
-    kappa = np.linalg.cond(A64) * growth(A, mode)
+    kappa = np.linalg.cond(A64)
     eye = np.eye(n)
     res = np.linalg.norm(A64 @ X.astype(np.float64) - eye, axis=(1, 2))
+    c_needed = res / (n * eps * kappa)
     bound = C_RES * n * eps * kappa
+    _record(n, mode, A.dtype, c_needed, (res > bound).sum())
     if Xref is not None:
-        bound = np.maximum(bound, 8.0 * np.linalg.norm(A64 @ Xref.astype(np.float64) - eye, axis=(1, 2)))
-    assert np.all(res <= bound), (what, float((res / bound).max()))
+        bound = np.maximum(bound, HATCH * np.linalg.norm(A64 @ Xref.astype(np.float64) - eye, axis=(1, 2)))
+    assert np.all(res <= bound), (what, float((res / bound).max()), float(c_needed.max()))
     if Xref is not None:
         Xt = np.linalg.inv(A64)
         scale = np.abs(Xt).max(axis=(1, 2))
         diff = np.abs(X.astype(np.float64) - Xref.astype(np.float64)).max(axis=(1, 2))
         err_ref = np.abs(Xref.astype(np.float64) - Xt).max(axis=(1, 2))
-        ebound = np.maximum(C_ELEM * n * eps * kappa * scale, 8.0 * err_ref)
+        ebound = np.maximum(C_ELEM * n * eps * kappa * scale, HATCH * err_ref)
         assert np.all(diff <= ebound), (what, float((diff / ebound).max()))
 
 
@@ -336,6 +354,98 @@ def test_headline_n32_1M_fp32_parallel(inputs):
 
 def test_config5_n32_1M_fp64_pivot(inputs):
     _full_size(32, 1_000_000, np.float64, 2, template(inputs, "mtrand64", 32, np.float64))
+
+
+def _nondominant_full_size(n, batch, dtype, mode):
+    """BASELINE full size on DISTINCT, NON-dominant uniform(0,1) matrices (SURVEY.md 8(d) set (i)): every matrix
+    has its own non-trivial pivot sequence.  A 50 k sample -- the first 20 k (first tiles), 10 k from the middle and
+    the last 20 k (the ragged end) -- is compared with the oracle: permutation vectors bit-exact, the
+    verify.hpp predicate's verdict equal except on borderline matrices."""
+    tdtype = torch.float32 if dtype == np.float32 else torch.float64
+    g = torch.Generator(device="cuda").manual_seed(4242 + n)
+    dA = torch.rand((batch, n, n), generator=g, device="cuda", dtype=tdtype)
+    idx = torch.cat([torch.arange(0, 20000), torch.arange(batch // 2 - 5000, batch // 2 + 5000),
+                     torch.arange(batch - 20000, batch)]).cuda()
+    A = dA[idx].cpu().numpy()
+    piv = torch.full((batch, n), -1, dtype=torch.int32, device="cuda")
+    lub.lu_batched_inplace(dA, piv, mode)
+    torch.cuda.synchronize()
+    X, p = dA[idx].cpu().numpy(), piv[idx].cpu().numpy()
+    with np.errstate(all="ignore"):
+        Xo, po = O.lu_batched(A, mode)
+    assert np.array_equal(p, po), ("pivots", n, mode, int((p != po).any(axis=1).sum()))
+    assert len(np.unique(po, axis=0)) > 40000    # the sample really exercises distinct, non-identity sequences
+    # verifyInv (templated/verify.hpp:57-96, threshold 1e-3) per matrix, for ours and for the oracle's result
+    A64 = A.astype(np.float64)
+    eye = np.eye(n)
+    with np.errstate(all="ignore"):
+        dev_g = np.abs(A64 @ X.astype(np.float64) - eye).max(axis=(1, 2))
+        dev_o = np.abs(A64 @ Xo.astype(np.float64) - eye).max(axis=(1, 2))
+    dev_g = np.where(np.isfinite(dev_g), dev_g, np.inf)
+    dev_o = np.where(np.isfinite(dev_o), dev_o, np.inf)
+    bad_g, bad_o = int((dev_g >= 1e-3).sum()), int((dev_o >= 1e-3).sum())
+    # a verdict may differ only on a borderline matrix: the other implementation within 8x of the threshold
+    flip = (dev_g >= 1e-3) != (dev_o >= 1e-3)
+    assert np.all(np.minimum(dev_g, dev_o)[flip] >= 1e-3 / 8), (n, mode, bad_g, bad_o, int(flip.sum()))
+    assert abs(bad_g - bad_o) <= max(25, bad_o // 4), (n, mode, bad_g, bad_o)
+    # and the library's own predicate counts what numpy counts (fp32 accumulation: allow the borderline band)
+    ok_l, bad_l, _ = lub.verify_inv(A, X)
+    near = int(((dev_g > 0.5e-3) & (dev_g < 2e-3)).sum())
+    assert ok_l + bad_l == len(A) and abs(bad_l - bad_g) <= near, (n, mode, bad_l, bad_g, near)
+    # ragged batch on the same data: one matrix short of a full last tile -> same results, next matrix untouched
+    g = torch.Generator(device="cuda").manual_seed(4242 + n)
+    dB = torch.rand((batch, n, n), generator=g, device="cuda", dtype=tdtype)
+    last = dB[batch - 1].clone()
+    lub.lu_batched_inplace(dB[: batch - 1], None, mode)
+    torch.cuda.synchronize()
+    assert bool((dB[batch - 1] == last).all())
+    assert bool((dB[batch - 20000: batch - 1] == dA[batch - 20000: batch - 1]).all())
+
+
+def test_headline_n32_1M_fp32_parallel_nondominant_pivots():
+    _nondominant_full_size(32, 1_000_000, np.float32, 2)
+
+
+def test_config3_n18_1M_fp32_parallel_nondominant_pivots():
+    _nondominant_full_size(18, 1_000_000, np.float32, 2)
+
+
+def test_config5_n32_1M_fp64_pivot_nondominant_pivots():
+    _nondominant_full_size(32, 1_000_000, np.float64, 2)
+
+
+def test_serial_n31_1M_fp32_nondominant_pivots():
+    _nondominant_full_size(31, 1_000_000, np.float32, 1)
+
+
+def test_raw_six_argument_entry_point_on_a_caller_stream():
+    """The exact north-star symbol, lu_batched_inplace(ptr, piv, n, batch, pivot_mode, dtype), called through
+    bare ctypes with device pointers on a stream installed by lu_batched_set_stream -- not through api.py, which
+    uses the _stream sibling."""
+    import ctypes
+    from matrixinversion_b200 import _lib
+    L = _lib.lib()
+    for n, dtype, code in ((32, np.float32, 0), (18, np.float32, 0), (32, np.float64, 1), (7, np.float64, 1)):
+        A = synthetic(n, 333, dtype)
+        with np.errstate(all="ignore"):
+            Xo, po = O.lu_batched(A, 2)
+        dA = torch.from_numpy(A).cuda()
+        piv = torch.full((333, n), -1, dtype=torch.int32, device="cuda")
+        torch.cuda.synchronize()
+        st = torch.cuda.Stream()
+        assert L.lu_batched_set_stream(ctypes.c_void_p(st.cuda_stream)) == 0
+        try:
+            rc = L.lu_batched_inplace(ctypes.c_void_p(dA.data_ptr()), ctypes.c_void_p(piv.data_ptr()), n, 333, 2, code)
+            assert rc == 0, L.lu_batched_last_error()
+            st.synchronize()
+        finally:
+            assert L.lu_batched_set_stream(None) == 0
+        assert np.array_equal(piv.cpu().numpy(), po)
+        good = np.isfinite(Xo).all(axis=(1, 2)) & (np.linalg.cond(A.astype(np.float64)) < 0.001 / EPS[np.dtype(dtype)])
+        check_values(A[good], dA.cpu().numpy()[good], Xo[good], ("raw abi", n, dtype), 2)
+    # bad arguments come back as codes through the same symbol
+    assert L.lu_batched_inplace(ctypes.c_void_p(dA.data_ptr()), None, 33, 1, 2, 0) == -1
+    assert L.lu_batched_inplace(ctypes.c_void_p(dA.data_ptr()), None, 7, 1, 9, 0) == -2
 
 
 def test_cublas_baseline_agrees():
