@@ -232,6 +232,24 @@ def ref_gpu_invert(A: np.ndarray, mode: int, want_piv: bool = False):
     return X, piv, ms.value
 
 
+def ref_gpu_time(dptr: int, n: int, batch: int, mode: int, dtype, reps: int = 5):
+    """Time the reference's own CUDA kernel (rebuilt for sm_100) on a DEVICE buffer of `batch` n x n matrices
+    (raw pointer, e.g. tensor.data_ptr()); the buffer is inverted in place `reps` times.  Returns
+    (ms_cold, ms_warm_best, matrices_processed) -- cold = first launch, the reference's own convention
+    (templated/luBatchedInplace.cu:71-82).  Checker-side only: never on the product path."""
+    suf = _suf(np.dtype(dtype))
+    name = "ref_%s_%s" % (_REF_KERNEL[mode], suf)
+    f = getattr(_ref(name), name + "_device")
+    f.restype = ctypes.c_int
+    f.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_longlong, ctypes.c_int,
+                  ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_longlong)]
+    c, w, p = ctypes.c_float(), ctypes.c_float(), ctypes.c_longlong()
+    rc = f(ctypes.c_void_p(dptr), None, n, batch, reps, ctypes.byref(c), ctypes.byref(w), ctypes.byref(p))
+    if rc != 0:
+        raise RuntimeError("reference kernel %s_device failed rc=%d" % (name, rc))
+    return c.value, w.value, p.value
+
+
 # ----------------------------------------------------------------------------------------
 # numpy twin (small cases only): same step order, same pivot rules, non-FMA arithmetic
 # ----------------------------------------------------------------------------------------

@@ -72,6 +72,62 @@ int run_one(const REF_T* hA, REF_T* hOut, int32_t* hPiv, long long batch, float*
 }
 }  // namespace
 
+// Timing entry (round 2): the reference kernel on a DEVICE buffer the caller owns, launched `reps` times in place
+// (A -> A^-1 -> A ...), each launch bracketed by CUDA events exactly as the reference's main() does
+// (templated/luBatchedInplace.cu:71-82).  Only whole blocks are launched: *processed = floor(batch / MPB) * MPB.
+// ms_cold = the first launch (the reference's convention: one cold launch per process), ms_warm = best of the rest.
+namespace {
+template <int N>
+int time_one(REF_T* dA, int* dP, long long batch, int reps, float* ms_cold, float* ms_warm, long long* processed) {
+    constexpr int TPM = N;
+    constexpr int T = (32 / N) * N;
+    constexpr int MPB = T / TPM;
+    const long long blocks = batch / MPB;
+    if (processed) *processed = blocks * MPB;
+    if (blocks == 0) return -1;
+    constexpr int shmem = MPB * (REF_SMEM(N, TPM)) * (int)sizeof(REF_T);
+    auto kern = batched_lu_subwarp<REF_T, N, TPM, MPB, INT_MAX>;
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, shmem) != cudaSuccess) return -2;
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    float cold = 0.f, warm = 1e30f;
+    cudaError_t err = cudaSuccess;
+    for (int r = 0; r < reps && err == cudaSuccess; ++r) {
+        cudaEventRecord(e0, 0);
+#ifdef REF_PIVOUT
+        kern<<<(unsigned)blocks, T, shmem>>>(dA, dP);
+#else
+        (void)dP;
+        kern<<<(unsigned)blocks, T, shmem>>>(dA);
+#endif
+        cudaEventRecord(e1, 0);
+        err = cudaEventSynchronize(e1);
+        if (err == cudaSuccess) err = cudaGetLastError();
+        float t = 0.f;
+        cudaEventElapsedTime(&t, e0, e1);
+        if (r == 0) cold = t; else if (t < warm) warm = t;
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    if (err != cudaSuccess) { fprintf(stderr, "ref kernel: %s\n", cudaGetErrorString(err)); return -3; }
+    if (ms_cold) *ms_cold = cold;
+    if (ms_warm) *ms_warm = (reps > 1) ? warm : cold;
+    return 0;
+}
+}  // namespace
+
+#define REF_CAT2(a, b) a##b
+#define REF_CAT(a, b) REF_CAT2(a, b)
+extern "C" int REF_CAT(REF_SYM, _device)(REF_T* dA, int* dP, int n, long long batch, int reps, float* ms_cold, float* ms_warm,
+                                          long long* processed) {
+    switch (n) {
+#define C(N) case N: return time_one<N>(dA, dP, batch, reps, ms_cold, ms_warm, processed);
+        C(1) C(2) C(3) C(4) C(5) C(6) C(7) C(8) C(9) C(10) C(11) C(12) C(13) C(14) C(15) C(16)
+        C(17) C(18) C(19) C(20) C(21) C(22) C(23) C(24) C(25) C(26) C(27) C(28) C(29) C(30) C(31) C(32)
+#undef C
+    }
+    return -1;
+}
+
 // Host buffers in, host buffers out.  Returns 0, or <0 on a CUDA error / bad n.
 extern "C" int REF_SYM(const REF_T* hA, REF_T* hOut, int32_t* hPiv, int n, long long batch, float* kernel_ms) {
     switch (n) {
