@@ -30,6 +30,16 @@ extern "C" {
 #define LUB_PIVOT_SERIAL 1   /* serial_pivot/luBatchedInplace.cuh:104-167 (find_pivot :22-36) */
 #define LUB_PIVOT_PARALLEL 2 /* parallel_pivot/luBatchedInplace.cuh:127-199 (find_pivot_parallel :12-44,
                                 including the candidates its tree drops for non-power-of-two N) */
+/* Extension: TRUE partial pivoting with LAPACK getrf semantics -- the arg-max is taken
+ * over the UPDATED column (the reference searches un-eliminated entries, parallel_pivot/luBatchedInplace.cuh:159),
+ * first maximum wins.  `piv` then receives LAPACK's ipiv (1-based: at step k the rows at positions k and
+ * ipiv[k]-1 were interchanged; identical to cublas<t>getrfBatched's PivotArray), and lu_batched_inplace_ex
+ * reports exactly-zero pivots in `info`.  This is the factorisation the reference's disabled check
+ * verifyLUwithPivoting (parallel_pivot/verify.hpp:157-242) is written for. */
+#define LUB_PIVOT_LAPACK 3
+/* layout of the batch in memory */
+#define LUB_LAYOUT_MATRIX_MAJOR 0      /* T A[batch][n][n]: the reference's (templated/luBatchedInplace.cuh:89-97) */
+#define LUB_LAYOUT_BATCH_INTERLEAVED 1 /* T A[n][n][batch]: element (i, j) of consecutive matrices is contiguous */
 /* dtype: the reference's FpType switch (templated/verify.hpp:9-10) */
 #define LUB_DTYPE_F32 0
 #define LUB_DTYPE_F64 1
@@ -66,6 +76,24 @@ int lu_batched_inplace(void* ptr, int32_t* piv, int n, int64_t batch, int pivot_
 /* Same, on an explicit stream (a cudaStream_t passed as void*; NULL = legacy default). */
 int lu_batched_inplace_stream(void* ptr, int32_t* piv, int n, int64_t batch, int pivot_mode, int dtype,
                               void* stream);
+
+/* Extended form of the hot path.
+ *   info    DEVICE int32[batch] or NULL: numerical status per matrix.  pivot_mode LAPACK: 0, or k (1-based) for the
+ *           first pivot U(k,k) that is exactly zero (the matrix is singular; its "inverse" is inf / NaN).  The
+ *           reference's variants have no status: with modes 0-2 the array is set to 0.
+ *   layout  LUB_LAYOUT_MATRIX_MAJOR, or LUB_LAYOUT_BATCH_INTERLEAVED (n <= 8, pivot modes NONE / LAPACK; piv and
+ *           info keep their [batch][n] / [batch] layouts): one lane per matrix, every access a fully coalesced
+ *           vector access across the batch.
+ *   stream  a cudaStream_t passed as void*. */
+int lu_batched_inplace_ex(void* ptr, int32_t* piv, int32_t* info, int n, int64_t batch, int pivot_mode, int dtype,
+                          int layout, void* stream);
+/* lu_batched_factor_inplace with `info` (matrix-major layout).  pivot_mode LAPACK: P A = L U exactly as getrf
+ * stores it, piv = ipiv. */
+int lu_batched_factor_inplace_ex(void* ptr, int32_t* piv, int32_t* info, int n, int64_t batch, int pivot_mode,
+                                 int dtype, void* stream);
+/* HOST helper: LAPACK swap lists ipiv[batch][n] (1-based) -> permutation vectors perm[batch][n] with the
+ * semantics of the other modes' piv (row i of P A is row perm[i] of A), e.g. for lu_batched_verify_lu. */
+int lu_batched_ipiv_to_perm(const int32_t* ipiv, int32_t* perm, int n, int64_t batch);
 
 /* LU factors only: stops where the reference's k-loop ends
  * (parallel_pivot/luBatchedInplace.cuh:156-186, serial_pivot/...cuh:130-160,

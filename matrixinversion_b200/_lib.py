@@ -16,7 +16,8 @@ _CSRC = os.path.join(_HERE, "csrc")
 LIB_PATH = os.path.join(_HERE, "liblubatched.so")
 CUBLAS_LIB_PATH = os.path.join(_HERE, "liblubatched_cublas.so")
 
-PIVOT_NONE, PIVOT_SERIAL, PIVOT_PARALLEL = 0, 1, 2
+PIVOT_NONE, PIVOT_SERIAL, PIVOT_PARALLEL, PIVOT_LAPACK = 0, 1, 2, 3
+LAYOUT_MATRIX_MAJOR, LAYOUT_BATCH_INTERLEAVED = 0, 1
 DTYPE_F32, DTYPE_F64 = 0, 1
 
 ERRORS = {
@@ -48,6 +49,9 @@ _FP = ctypes.POINTER(ctypes.c_float)
 SIGNATURES = {
     "lu_batched_inplace": (ctypes.c_int, [_P, _P, ctypes.c_int, ctypes.c_int64, ctypes.c_int, ctypes.c_int]),
     "lu_batched_inplace_stream": (ctypes.c_int, [_P, _P, ctypes.c_int, ctypes.c_int64, ctypes.c_int, ctypes.c_int, _P]),
+    "lu_batched_inplace_ex": (ctypes.c_int, [_P, _P, _P, ctypes.c_int, ctypes.c_int64, ctypes.c_int, ctypes.c_int, ctypes.c_int, _P]),
+    "lu_batched_factor_inplace_ex": (ctypes.c_int, [_P, _P, _P, ctypes.c_int, ctypes.c_int64, ctypes.c_int, ctypes.c_int, _P]),
+    "lu_batched_ipiv_to_perm": (ctypes.c_int, [_P, _P, ctypes.c_int, ctypes.c_int64]),
     "lu_batched_factor_inplace": (ctypes.c_int, [_P, _P, ctypes.c_int, ctypes.c_int64, ctypes.c_int, ctypes.c_int]),
     "lu_batched_factor_inplace_stream": (ctypes.c_int, [_P, _P, ctypes.c_int, ctypes.c_int64, ctypes.c_int, ctypes.c_int, _P]),
     "lu_batched_set_stream": (ctypes.c_int, [_P]),

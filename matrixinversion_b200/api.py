@@ -12,6 +12,7 @@ CPU fallback: the CUDA library must load and a GPU must be present for every com
     templated/         "none"      (0)
     serial_pivot/      "serial"    (1)
     parallel_pivot/    "parallel"  (2)
+    (extension)        "lapack"    (3)   true partial pivoting, LAPACK ipiv + info
 """
 from __future__ import annotations
 
@@ -24,10 +25,14 @@ from dataclasses import dataclass
 import numpy as np
 
 from . import _lib
-from ._lib import DTYPE_F32, DTYPE_F64, PIVOT_NONE, PIVOT_PARALLEL, PIVOT_SERIAL, LubError, check
+from ._lib import (DTYPE_F32, DTYPE_F64, LAYOUT_BATCH_INTERLEAVED, LAYOUT_MATRIX_MAJOR, PIVOT_LAPACK, PIVOT_NONE, PIVOT_PARALLEL,
+                   PIVOT_SERIAL, LubError, check)
 
 PIVOT_MODES = {"none": PIVOT_NONE, "serial": PIVOT_SERIAL, "parallel": PIVOT_PARALLEL,
-               "templated": PIVOT_NONE, "serial_pivot": PIVOT_SERIAL, "parallel_pivot": PIVOT_PARALLEL}
+               "templated": PIVOT_NONE, "serial_pivot": PIVOT_SERIAL, "parallel_pivot": PIVOT_PARALLEL,
+               "lapack": PIVOT_LAPACK, "partial": PIVOT_LAPACK}
+LAYOUTS = {"matrix": LAYOUT_MATRIX_MAJOR, "matrix_major": LAYOUT_MATRIX_MAJOR,
+           "interleaved": LAYOUT_BATCH_INTERLEAVED, "batch_interleaved": LAYOUT_BATCH_INTERLEAVED}
 
 
 def _mode(pivot_mode) -> int:
@@ -70,9 +75,14 @@ def _check_batch(shape):
 # the hot path
 # ------------------------------------------------------------------------------------------
 
-def lu_batched_inplace(A, piv=None, pivot_mode="parallel", stream=None):
+def lu_batched_inplace(A, piv=None, pivot_mode="parallel", stream=None, info=None, layout="matrix"):
     """Invert every matrix of A[batch, n, n] in place (the `batched_lu_subwarp` launch,
     parallel_pivot/luBatchedInplace.cu:127).
+
+    info: optional CUDA int32 [batch] tensor (lu_batched_inplace_ex): with pivot_mode "lapack" 0 or the 1-based
+       index of the first exactly-zero pivot; the reference's modes have no status and write 0.
+    layout: "matrix" (the reference's A[batch][n][n]) or "interleaved" -- then A is a CUDA tensor of shape
+       [n, n, batch] (element (i, j) of consecutive matrices contiguous), n <= 8.
 
     A: contiguous CUDA torch tensor (float32/float64) -> asynchronous launch on `stream`
        (default: torch's current stream); or a C-contiguous numpy array -> the chunked
@@ -83,7 +93,16 @@ def lu_batched_inplace(A, piv=None, pivot_mode="parallel", stream=None):
     """
     L = _lib.lib()
     mode = _mode(pivot_mode)
-    batch, n = _check_batch(A.shape)
+    try:
+        lay = LAYOUTS[layout] if isinstance(layout, str) else int(layout)
+    except KeyError:
+        raise LubError(-4, "unknown layout %r" % (layout,)) from None
+    if lay == LAYOUT_BATCH_INTERLEAVED:
+        if len(A.shape) != 3 or A.shape[0] != A.shape[1]:
+            raise LubError(-4, "the interleaved layout expects a [n, n, batch] tensor, got shape %s" % (tuple(A.shape),))
+        n, batch = int(A.shape[0]), int(A.shape[2])
+    else:
+        batch, n = _check_batch(A.shape)
     if _is_torch(A):
         import torch
         if not A.is_cuda:
@@ -91,6 +110,12 @@ def lu_batched_inplace(A, piv=None, pivot_mode="parallel", stream=None):
         if not A.is_contiguous():
             raise LubError(-4, "A must be contiguous")
         dt = _dtype_code(A.dtype)
+        iptr = None
+        if info is not None:
+            if not (info.is_cuda and info.is_contiguous() and info.dtype == torch.int32 and tuple(info.shape) == (batch,)
+                    and info.device == A.device):
+                raise LubError(-4, "info must be a contiguous CUDA int32 [batch] tensor on A's device")
+            iptr = info.data_ptr()
         pptr = None
         if piv is not None:
             if not (piv.is_cuda and piv.is_contiguous() and piv.dtype == torch.int32 and tuple(piv.shape) == (batch, n)):
@@ -101,8 +126,13 @@ def lu_batched_inplace(A, piv=None, pivot_mode="parallel", stream=None):
         with torch.cuda.device(A.device):
             s = stream if stream is not None else torch.cuda.current_stream(A.device)
             sp = s.cuda_stream if hasattr(s, "cuda_stream") else int(s)
-            check(L.lu_batched_inplace_stream(A.data_ptr(), pptr, n, batch, mode, dt, sp))
+            if iptr is None and lay == LAYOUT_MATRIX_MAJOR:
+                check(L.lu_batched_inplace_stream(A.data_ptr(), pptr, n, batch, mode, dt, sp))
+            else:
+                check(L.lu_batched_inplace_ex(A.data_ptr(), pptr, iptr, n, batch, mode, dt, lay, sp))
         return A
+    if info is not None or lay != LAYOUT_MATRIX_MAJOR:
+        raise LubError(-4, "info / layout are device-side options: pass CUDA tensors")
     if not isinstance(A, np.ndarray) or not A.flags.c_contiguous or not A.flags.writeable:
         raise LubError(-4, "A must be a CUDA torch tensor or a writable C-contiguous numpy array")
     dt = _dtype_code(A.dtype)
@@ -115,7 +145,16 @@ def lu_batched_inplace(A, piv=None, pivot_mode="parallel", stream=None):
     return A
 
 
-def lu_batched_factor_inplace(A, piv=None, pivot_mode="parallel", stream=None):
+def ipiv_to_perm(ipiv: np.ndarray) -> np.ndarray:
+    """LAPACK swap lists (pivot_mode "lapack": 1-based ipiv[batch, n]) -> the permutation vectors the other modes
+    write to piv (row i of P A is row perm[i] of A), e.g. for verify_lu."""
+    ipiv = np.ascontiguousarray(ipiv, dtype=np.int32)
+    perm = np.empty_like(ipiv)
+    check(_lib.lib().lu_batched_ipiv_to_perm(ipiv.ctypes.data, perm.ctypes.data, ipiv.shape[1], ipiv.shape[0]))
+    return perm
+
+
+def lu_batched_factor_inplace(A, piv=None, pivot_mode="parallel", stream=None, info=None):
     """LU factors only, in place: the state of the reference's shared-memory matrix
     after its k-loop (parallel_pivot/luBatchedInplace.cuh:156-186), which upstream's disabled
     `verifyLU` / `verifyLUwithPivoting` are written for.  A: contiguous CUDA torch tensor
@@ -137,7 +176,13 @@ def lu_batched_factor_inplace(A, piv=None, pivot_mode="parallel", stream=None):
     with torch.cuda.device(A.device):
         s = stream if stream is not None else torch.cuda.current_stream(A.device)
         sp = s.cuda_stream if hasattr(s, "cuda_stream") else int(s)
-        check(L.lu_batched_factor_inplace_stream(A.data_ptr(), pptr, n, batch, mode, _dtype_code(A.dtype), sp))
+        if info is None:
+            check(L.lu_batched_factor_inplace_stream(A.data_ptr(), pptr, n, batch, mode, _dtype_code(A.dtype), sp))
+        else:
+            if not (info.is_cuda and info.is_contiguous() and info.dtype == torch.int32 and tuple(info.shape) == (batch,)
+                    and info.device == A.device):
+                raise LubError(-4, "info must be a contiguous CUDA int32 [batch] tensor on A's device")
+            check(L.lu_batched_factor_inplace_ex(A.data_ptr(), pptr, info.data_ptr(), n, batch, mode, _dtype_code(A.dtype), sp))
     return A
 
 

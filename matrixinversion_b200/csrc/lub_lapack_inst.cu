@@ -1,0 +1,43 @@
+// lub_lapack_inst.cu -- instantiations and launcher of pivot_mode 3 (lub_lapack.cuh), one translation unit per
+// dtype.  Compile with -DLUB_T=float|double -DLUB_TN=f32|f64.
+#include "lub_launch.cuh"
+#include "lub_lapack.cuh"
+
+namespace lub {
+
+template <typename T, int N, bool LUONLY>
+static cudaError_t launch_lapack_n(void* A, int32_t* ipiv, int32_t* info, long long batch, int threads_req, cudaStream_t stream,
+                                   LaunchInfo* li, int flags, cudaEvent_t ev0) {
+    using L = LapackLayout<T, N>;
+    int dev = 0;
+    cudaError_t err = cudaGetDevice(&dev);
+    if (err != cudaSuccess) return err;
+    if (dev < 0 || dev >= kMaxDevices) return cudaErrorInvalidDevice;
+    static KernelCache cache[kMaxDevices];
+    auto kern = lub_lapack_kernel<T, N, LUONLY>;
+    LaunchCtx x{batch, threads_req > 0 ? threads_req : 256, stream, li, (flags & kLaunchDryRun) != 0, ev0, dev};
+    return run_kernel(kern, cache[dev], x, kMaxThreads, [](int w) { return L::smem_bytes(w); }, L::MPW, L::G,
+                      LUONLY ? "lub_lapack_kernel<LUONLY>" : "lub_lapack_kernel", [&](unsigned blocks, int smem) {
+                          cudaError_t e = ev0 ? cudaEventRecord(ev0, stream) : cudaSuccess;
+                          if (e != cudaSuccess) return e;
+                          kern<<<blocks, x.threads, smem, stream>>>(static_cast<T*>(A), ipiv, info, batch);
+                          return cudaGetLastError();
+                      });
+}
+
+#define LUB_LAPACK_CAT_(a) launch_lapack_##a
+#define LUB_LAPACK_CAT(a) LUB_LAPACK_CAT_(a)
+cudaError_t LUB_LAPACK_CAT(LUB_TN)(void* A, int32_t* ipiv, int32_t* info, int n, long long batch, int threads, cudaStream_t stream,
+                                   LaunchInfo* li, int flags, cudaEvent_t ev0) {
+    const bool lu = (flags & kLaunchLuOnly) != 0;
+    switch (n) {
+#define C(N) case N: return lu ? launch_lapack_n<LUB_T, N, true>(A, ipiv, info, batch, threads, stream, li, flags, ev0) \
+                               : launch_lapack_n<LUB_T, N, false>(A, ipiv, info, batch, threads, stream, li, flags, ev0);
+        C(1) C(2) C(3) C(4) C(5) C(6) C(7) C(8) C(9) C(10) C(11) C(12) C(13) C(14) C(15) C(16)
+        C(17) C(18) C(19) C(20) C(21) C(22) C(23) C(24) C(25) C(26) C(27) C(28) C(29) C(30) C(31) C(32)
+#undef C
+    }
+    return cudaErrorInvalidValue;
+}
+
+}  // namespace lub

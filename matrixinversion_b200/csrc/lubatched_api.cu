@@ -25,6 +25,14 @@ LUB_DECL(f32, 0) LUB_DECL(f32, 1) LUB_DECL(f32, 2)
 LUB_DECL(f64, 0) LUB_DECL(f64, 1) LUB_DECL(f64, 2)
 #undef LUB_DECL
 
+// pivot_mode 3 (lub_lapack_inst.cu)
+cudaError_t launch_lapack_f32(void*, int32_t*, int32_t*, int, long long, int, cudaStream_t, LaunchInfo*, int, cudaEvent_t);
+cudaError_t launch_lapack_f64(void*, int32_t*, int32_t*, int, long long, int, cudaStream_t, LaunchInfo*, int, cudaEvent_t);
+
+// batch-interleaved layout (lub_interleaved_inst.cu)
+cudaError_t launch_interleaved_f32(void*, int32_t*, int32_t*, int, long long, int, cudaStream_t, cudaEvent_t);
+cudaError_t launch_interleaved_f64(void*, int32_t*, int32_t*, int, long long, int, cudaStream_t, cudaEvent_t);
+
 static LaunchFn find_launcher(int n, int mode, int dtype) {
     using Getter = LaunchFn (*)(int);
 #define LUB_ROW(TN, M) { lub_get_##TN##_m##M##_q0, lub_get_##TN##_m##M##_q1, lub_get_##TN##_m##M##_q2, lub_get_##TN##_m##M##_q3 }
@@ -59,7 +67,7 @@ int cuda_fail(cudaError_t e, const char* where) {
 
 int check_args(int n, int64_t batch, int mode, int dtype) {
     if (n < 1 || n > 32) return fail(LUB_ERR_BAD_N, "n must be in [1, 32]");
-    if (mode < LUB_PIVOT_NONE || mode > LUB_PIVOT_PARALLEL) return fail(LUB_ERR_BAD_MODE, "pivot_mode must be 0 (none), 1 (serial) or 2 (parallel)");
+    if (mode < LUB_PIVOT_NONE || mode > LUB_PIVOT_LAPACK) return fail(LUB_ERR_BAD_MODE, "pivot_mode must be 0 (none), 1 (serial), 2 (parallel) or 3 (LAPACK partial pivoting)");
     if (dtype != LUB_DTYPE_F32 && dtype != LUB_DTYPE_F64) return fail(LUB_ERR_BAD_DTYPE, "dtype must be 0 (fp32) or 1 (fp64)");
     if (batch < 0) return fail(LUB_ERR_BAD_ARG, "batch must be >= 0");
     return LUB_OK;
@@ -69,7 +77,7 @@ size_t esize(int dtype) { return dtype == LUB_DTYPE_F32 ? 4 : 8; }
 
 // flags: lub::kLaunchDryRun | lub::kLaunchLuOnly
 int launch_on(void* ptr, int32_t* piv, int n, int64_t batch, int mode, int dtype, cudaStream_t s,
-              lub::LaunchInfo* info, int flags) {
+              lub::LaunchInfo* info, int flags, int32_t* status = nullptr) {
     const bool dry = (flags & lub::kLaunchDryRun) != 0;
     int rc = check_args(n, batch, mode, dtype);
     if (rc != LUB_OK) return rc;
@@ -77,8 +85,8 @@ int launch_on(void* ptr, int32_t* piv, int n, int64_t batch, int mode, int dtype
         if (ptr == nullptr) return fail(LUB_ERR_BAD_ARG, "ptr is NULL");
         if (reinterpret_cast<uintptr_t>(ptr) % esize(dtype)) return fail(LUB_ERR_BAD_ARG, "ptr is not aligned to the element size");
     }
-    lub::LaunchFn fn = lub::find_launcher(n, mode, dtype);
-    if (!fn) return fail(LUB_ERR_BAD_N, "no kernel for this n");
+    lub::LaunchFn fn = (mode == LUB_PIVOT_LAPACK) ? nullptr : lub::find_launcher(n, mode, dtype);
+    if (!fn && mode != LUB_PIVOT_LAPACK) return fail(LUB_ERR_BAD_N, "no kernel for this n");
     const bool timed = g_timing && !dry && batch > 0;
     int dev = 0;
     if (timed) {
@@ -89,7 +97,37 @@ int launch_on(void* ptr, int32_t* piv, int n, int64_t batch, int mode, int dtype
     }
     // the launcher records the start event itself, after its one-time preparation (function attributes,
     // occupancy query, tensor-map encode): the interval is the kernel's, also on the first call
-    cudaError_t e = fn(ptr, piv, (long long)batch, g_threads, s, info, flags, timed ? g_ev[dev][0] : nullptr);
+    cudaError_t e;
+    if (mode == LUB_PIVOT_LAPACK) {
+        e = (dtype == LUB_DTYPE_F32 ? lub::launch_lapack_f32 : lub::launch_lapack_f64)(ptr, piv, status, n, (long long)batch, g_threads, s, info, flags,
+                                                                                     timed ? g_ev[dev][0] : nullptr);
+    } else {
+        // the reference's variants have no numerical status: a status array given with modes 0-2 reads 0
+        if (status && !dry && batch > 0) CU(cudaMemsetAsync(status, 0, (size_t)batch * sizeof(int32_t), s));
+        e = fn(ptr, piv, (long long)batch, g_threads, s, info, flags, timed ? g_ev[dev][0] : nullptr);
+    }
+    if (e != cudaSuccess) return cuda_fail(e, "kernel launch");
+    if (timed) { CU(cudaEventRecord(g_ev[dev][1], s)); g_ev_dev = dev; }
+    return LUB_OK;
+}
+
+int launch_interleaved(void* ptr, int32_t* piv, int32_t* status, int n, int64_t batch, int mode, int dtype, cudaStream_t s) {
+    int rc = check_args(n, batch, mode, dtype);
+    if (rc != LUB_OK) return rc;
+    if (n > 8) return fail(LUB_ERR_BAD_N, "the batch-interleaved layout holds one matrix per lane: n must be in [1, 8]");
+    if (batch == 0) return LUB_OK;
+    if (ptr == nullptr) return fail(LUB_ERR_BAD_ARG, "ptr is NULL");
+    if (reinterpret_cast<uintptr_t>(ptr) % esize(dtype)) return fail(LUB_ERR_BAD_ARG, "ptr is not aligned to the element size");
+    const bool timed = g_timing;
+    int dev = 0;
+    if (timed) {
+        CU(cudaGetDevice(&dev));
+        if (dev < 0 || dev >= lub::kMaxDevices) return fail(LUB_ERR_CUDA, "device index out of range");
+        if (!g_ev[dev][0]) { CU(cudaEventCreate(&g_ev[dev][0])); CU(cudaEventCreate(&g_ev[dev][1])); }
+        g_ev_dev = -1;
+    }
+    cudaError_t e = (dtype == LUB_DTYPE_F32 ? lub::launch_interleaved_f32 : lub::launch_interleaved_f64)(
+        ptr, piv, status, n, (long long)batch, mode, s, timed ? g_ev[dev][0] : nullptr);
     if (e != cudaSuccess) return cuda_fail(e, "kernel launch");
     if (timed) { CU(cudaEventRecord(g_ev[dev][1], s)); g_ev_dev = dev; }
     return LUB_OK;
@@ -265,6 +303,33 @@ int lu_batched_inplace_stream(void* ptr, int32_t* piv, int n, int64_t batch, int
 
 int lu_batched_inplace(void* ptr, int32_t* piv, int n, int64_t batch, int pivot_mode, int dtype) {
     return launch_on(ptr, piv, n, batch, pivot_mode, dtype, g_stream, nullptr, 0);
+}
+
+int lu_batched_inplace_ex(void* ptr, int32_t* piv, int32_t* info, int n, int64_t batch, int pivot_mode, int dtype, int layout, void* stream) {
+    if (layout == LUB_LAYOUT_BATCH_INTERLEAVED) return launch_interleaved(ptr, piv, info, n, batch, pivot_mode, dtype, static_cast<cudaStream_t>(stream));
+    if (layout != LUB_LAYOUT_MATRIX_MAJOR) return fail(LUB_ERR_BAD_ARG, "layout must be 0 (matrix-major) or 1 (batch-interleaved)");
+    return launch_on(ptr, piv, n, batch, pivot_mode, dtype, static_cast<cudaStream_t>(stream), nullptr, 0, info);
+}
+
+int lu_batched_factor_inplace_ex(void* ptr, int32_t* piv, int32_t* info, int n, int64_t batch, int pivot_mode, int dtype, void* stream) {
+    return launch_on(ptr, piv, n, batch, pivot_mode, dtype, static_cast<cudaStream_t>(stream), nullptr, lub::kLaunchLuOnly, info);
+}
+
+int lu_batched_ipiv_to_perm(const int32_t* ipiv, int32_t* perm, int n, int64_t batch) {
+    if (n < 1 || batch < 0 || ((!ipiv || !perm) && batch)) return fail(LUB_ERR_BAD_ARG, "bad arguments");
+    int bad = 0;
+#pragma omp parallel for schedule(static) reduction(| : bad)
+    for (int64_t b = 0; b < batch; ++b) {
+        int32_t* p = perm + b * n;
+        const int32_t* ip = ipiv + b * n;
+        for (int i = 0; i < n; ++i) p[i] = i;
+        for (int k = 0; k < n; ++k) {
+            const int q = ip[k] - 1;
+            if (q < k || q >= n) { bad = 1; continue; }
+            const int32_t t = p[k]; p[k] = p[q]; p[q] = t;
+        }
+    }
+    return bad ? fail(LUB_ERR_BAD_ARG, "ipiv holds an entry outside [k + 1, n]") : LUB_OK;
 }
 
 int lu_batched_factor_inplace_stream(void* ptr, int32_t* piv, int n, int64_t batch, int pivot_mode, int dtype, void* stream) {

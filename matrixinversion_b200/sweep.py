@@ -20,7 +20,13 @@ What is kept:
 What is fixed: the reference's parser `break`s on the "Kernel execution time" line, which is
 printed before "Incorrect inversions", so its sweep never records correctness.
 Here `incorrect_inversions` is the verifyInv-compatible count of every run.
-Extra keys (additive): gbps, matrices_per_s, gflops_2n3, frac_hbm_roofline, cublas_ms (--cublas).
+  * the per-configuration Nsight Compute capture (run.py:90-119) with `--ncu`: the same sections, one report per
+    configuration under benchmark_results/ncu_profiles/<100k|500k|1M>/profile_m{N}_n{batch}_t{T}.ncu-rep; the profiled
+    process is this module in `--one-launch` mode (one cold launch, what ./custom did).  Clocks are NOT locked
+    (`--clock-control none`): the reference's `base` lock changes what is measured and is not allowed on shared boxes.
+Extra keys (additive): gbps, matrices_per_s, gflops_2n3, frac_hbm_roofline, cublas_ms (--cublas), and whatever a
+`--compare module:function` hook returns (used by the test tree to put the reference's own kernels, rebuilt for
+sm_100, next to ours: function(device_ptr, n, batch, mode, dtype_name) -> dict).
 Several GPUs (BASELINE config 4 "at 1/2/4/8 B200"): launched under
 `python -m torch.distributed.run --nproc-per-node G -m matrixinversion_b200.sweep ...` every rank
 inverts its contiguous slice of each batch (sharding.shard_range: strong scaling, the batch sizes of
@@ -32,9 +38,12 @@ from __future__ import annotations
 
 import argparse
 import ctypes
+import importlib
 import json
 import os
 import shutil
+import subprocess
+import sys
 
 import numpy as np
 
@@ -44,14 +53,41 @@ from .sharding import reduce_verdict, shard_range
 BATCH_NAMES = {100000: "100k", 500000: "500k", 1000000: "1M"}
 
 
-def create_output_directories(base="benchmark_results"):
-    """run.py:9-22."""
-    if os.path.exists(base):
-        shutil.rmtree(base)
+MARKER = ".lubatched_sweep"
+
+
+def create_output_directories(base="benchmark_results", force=False):
+    """run.py:9-22, made safe for a user-chosen path: the reference wipes its fixed `benchmark_results`
+    directory; here only the two sub-directories the sweep itself creates are ever removed, and only when
+    the directory carries the marker a previous sweep left (or --force is given)."""
     ncu_dir, runtime_dir = os.path.join(base, "ncu_profiles"), os.path.join(base, "runtime_results")
-    os.makedirs(ncu_dir)
-    os.makedirs(runtime_dir)
+    stale = [d for d in (ncu_dir, runtime_dir) if os.path.exists(d)]
+    if stale and not (force or os.path.exists(os.path.join(base, MARKER))):
+        raise SystemExit("sweep: %s holds results this sweep did not create (no %s marker); move them away or pass --force"
+                         % (base, MARKER))
+    for d in stale:
+        shutil.rmtree(d)
+    os.makedirs(ncu_dir, exist_ok=True)
+    os.makedirs(runtime_dir, exist_ok=True)
+    with open(os.path.join(base, MARKER), "w") as f:
+        f.write("created by matrixinversion_b200.sweep\n")
     return base, ncu_dir, runtime_dir
+
+
+def run_ncu_profile(n, batch, num_threads, ncu_dir, variant, dtype, input_path):
+    """The reference's capture (templated/run.py:90-119): same sections and sampling options, one report per
+    configuration; ./custom is replaced by this module's --one-launch mode."""
+    profile_path = os.path.join(ncu_dir, "profile_m%d_n%d_t%d" % (n, batch, num_threads))
+    cmd = ["ncu", "--set=full", "--import-source", "yes", "--target-processes", "all", "--replay-mode", "kernel",
+           "--section", "InstructionStats", "--section", "LaunchStats", "--section", "MemoryWorkloadAnalysis",
+           "--section", "SchedulerStats", "--section", "SourceCounters", "--section", "SpeedOfLight",
+           "--sampling-interval", "auto", "--sampling-max-passes", "5", "--sampling-buffer-size", "33554432",
+           "--clock-control", "none", "--kernel-name", "regex:lub_", "--launch-count", "1", "-f", "-o", profile_path,
+           sys.executable, "-m", "matrixinversion_b200.sweep", "--one-launch", "--variant", variant, "--dtype", str(np.dtype(dtype)),
+           "--sizes", str(n), "--batches", str(batch), "--input", input_path]
+    subprocess.run(cmd, check=True, stdout=subprocess.DEVNULL)
+    print("NCU profile saved to %s" % profile_path)
+    return profile_path + ".ncu-rep"
 
 
 def result_key(matrix_size, num_matrices, num_threads):
@@ -90,7 +126,7 @@ def _max_over_ranks(ms, world):
     return float(t.item())
 
 
-def run_config(n, batch, mode, dtype, template, runs, warm=False, cublas=False, peak_gbps=None, rank=0, world=1):
+def run_config(n, batch, mode, dtype, template, runs, warm=False, cublas=False, peak_gbps=None, rank=0, world=1, compare=None):
     """`runs` cold single launches of one configuration; returns the JSON entry.  With world > 1 this
     rank works on its slice of the batch; times are maxima over ranks, incorrect counts sums."""
     import torch
@@ -144,6 +180,10 @@ def run_config(n, batch, mode, dtype, template, runs, warm=False, cublas=False, 
             extra["cublas_ms"] = t1.value + t2.value
             extra["cublas_getri_share"] = t2.value / (t1.value + t2.value)
             extra["speedup_vs_cublas"] = (t1.value + t2.value) / best
+    if compare is not None and world == 1:
+        A.copy_(orig)
+        torch.cuda.synchronize()
+        extra.update(compare(A.data_ptr(), n, batch, api._mode(mode), str(np.dtype(dtype))))
     return make_entry(n, batch, geo.threads_per_block, runtimes, incorrect, extra)
 
 
@@ -159,12 +199,28 @@ def main(argv=None):
     ap.add_argument("--warm", action="store_true")
     ap.add_argument("--cublas", action="store_true")
     ap.add_argument("--peak-gbps", type=float, default=None)
+    ap.add_argument("--ncu", action="store_true", help="one Nsight Compute report per configuration (templated/run.py:90-119)")
+    ap.add_argument("--one-launch", action="store_true", help="one cold launch of the first size / batch and exit (what --ncu profiles)")
+    ap.add_argument("--compare", default="", help="module:function timing hook, see the module docstring")
+    ap.add_argument("--force", action="store_true", help="replace result directories this sweep did not create")
     a = ap.parse_args(argv)
 
     lo, _, hi = a.sizes.partition("-")
     sizes = range(int(lo), int(hi or lo) + 1)
     dtype = np.dtype(a.dtype)
     rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+    if a.one_launch:
+        import torch
+        n, batch = sizes[0], int(a.batches.split(",")[0])
+        T = api.read_template(a.input, n, dtype)
+        A = torch.from_numpy(T).cuda().unsqueeze(0).expand(batch, n, n).contiguous()
+        api.lu_batched_inplace(A, None, a.variant)
+        torch.cuda.synchronize()
+        return 0
+    compare = None
+    if a.compare:
+        mod, _, fn = a.compare.partition(":")
+        compare = getattr(importlib.import_module(mod), fn)
     if world > 1:  # one process per GPU (torch.distributed.run); NCCL only for the scalar reductions
         import torch
         import torch.distributed as dist
@@ -172,7 +228,7 @@ def main(argv=None):
         torch.cuda.set_device(local)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     if rank == 0:
-        base, ncu_dir, runtime_dir = create_output_directories(a.out)
+        base, ncu_dir, runtime_dir = create_output_directories(a.out, a.force)
     else:
         base, ncu_dir, runtime_dir = a.out, os.path.join(a.out, "ncu_profiles"), os.path.join(a.out, "runtime_results")
     results = {}
@@ -188,9 +244,12 @@ def main(argv=None):
                 if rank == 0:
                     print("\nTesting configuration: Matrix Size=%d, Num Matrices=%d" % (n, batch))
                 template = api.read_template(a.input, n, dtype)
-                entry = run_config(n, batch, a.variant, dtype, template, a.runs, a.warm, a.cublas, a.peak_gbps, rank, world)
+                entry = run_config(n, batch, a.variant, dtype, template, a.runs, a.warm, a.cublas, a.peak_gbps, rank, world, compare)
                 if rank == 0:
                     print("Number of threads: %d" % entry["num_threads"])
+                    if a.ncu and world == 1:
+                        entry["ncu_report"] = run_ncu_profile(n, batch, entry["num_threads"], os.path.join(ncu_dir, name), a.variant,
+                                                              dtype, a.input)
                     results[result_key(n, batch, entry["num_threads"])] = entry
                     save_results(results, os.path.join(out_dir, "benchmark_results_%s.json" % name))
     except Exception as e:  # keep what we have, like the reference (run.py:252-260)

@@ -250,6 +250,30 @@ def ref_gpu_time(dptr: int, n: int, batch: int, mode: int, dtype, reps: int = 5)
     return c.value, w.value, p.value
 
 
+def lapack_getrf(A: np.ndarray):
+    """LAPACK's own getrf (through scipy) on every matrix of A[b, n, n], in A's precision: the external truth for
+    pivot_mode 3.  Returns (LU, ipiv 1-based int32 [b, n], info int32 [b])."""
+    from scipy.linalg import get_lapack_funcs
+    A = np.ascontiguousarray(A)
+    b, n, _ = A.shape
+    (getrf,) = get_lapack_funcs(("getrf",), (A[0],))
+    LU = np.empty_like(A)
+    ipiv = np.empty((b, n), np.int32)
+    info = np.empty(b, np.int32)
+    for i in range(b):
+        lu, piv, inf = getrf(A[i])
+        LU[i], ipiv[i], info[i] = lu, piv + 1, inf
+    return LU, ipiv, info
+
+
+def sweep_compare_hook(dptr, n, batch, mode, dtype_name):
+    """`--compare oracle.oracle:sweep_compare_hook` of the sweep drivers: the reference kernel's times on the sweep's buffer."""
+    if mode == MODE_PARALLEL and dtype_name == "float64" and n % 2:
+        return {"reference_gpu_error": "reference bug: misaligned shared-memory carve for odd N in fp64 (parallel_pivot/luBatchedInplace.cuh:142)"}
+    cold, warm, done = ref_gpu_time(dptr, n, batch, mode, np.dtype(dtype_name), reps=3)
+    return {"reference_gpu_ms_cold": cold, "reference_gpu_ms_warm": warm, "reference_gpu_matrices": done}
+
+
 # ----------------------------------------------------------------------------------------
 # numpy twin (small cases only): same step order, same pivot rules, non-FMA arithmetic
 # ----------------------------------------------------------------------------------------

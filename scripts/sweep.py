@@ -17,6 +17,7 @@ ap.add_argument("--batch", type=int, default=1_000_000)
 ap.add_argument("--ns", default=",".join(str(i) for i in range(1, 33)))
 ap.add_argument("--iters", type=int, default=5)
 ap.add_argument("--cublas", action="store_true")
+ap.add_argument("--refgpu", action="store_true", help="also time the reference's own kernel rebuilt for sm_100 (oracle/_ref)")
 ap.add_argument("--threads", type=int, default=0)
 ap.add_argument("--out", default="")
 a = ap.parse_args()
@@ -58,6 +59,14 @@ for n in [int(x) for x in a.ns.split(",")]:
         row["cublas_ms"] = best
         row["speedup_vs_cublas"] = best / ms
         del dst
+    if a.refgpu:
+        from oracle import oracle as O  # checker side: dev script, not the product
+        mode_code = {"none": 0, "serial": 1, "parallel": 2}[a.mode]
+        A.copy_(orig); torch.cuda.synchronize()
+        h = O.sweep_compare_hook(A.data_ptr(), n, a.batch, mode_code, "float32" if a.dtype == "f32" else "float64")
+        row.update(h)
+        if "reference_gpu_ms_warm" in h:
+            row["speedup_vs_reference_gpu"] = h["reference_gpu_ms_warm"] * (a.batch / max(h["reference_gpu_matrices"], 1)) / ms
     rows.append(row)
     print(json.dumps(row), flush=True)
     del A, orig

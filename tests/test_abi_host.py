@@ -56,7 +56,10 @@ def test_argument_errors_are_codes_not_exits():
     L = _lib.lib()
     assert L.lu_batched_inplace(None, None, 0, 1, 0, 0) == -1     # n out of range
     assert L.lu_batched_inplace(None, None, 33, 1, 0, 0) == -1
-    assert L.lu_batched_inplace(None, None, 4, 1, 3, 0) == -2     # mode
+    assert L.lu_batched_inplace(None, None, 4, 1, 4, 0) == -2     # mode (3 = LAPACK partial pivoting is valid)
+    assert L.lu_batched_inplace(None, None, 4, 1, -1, 0) == -2
+    assert L.lu_batched_inplace_ex(None, None, None, 4, 1, 0, 0, 7, None) == -4   # layout
+    assert L.lu_batched_inplace_ex(None, None, None, 9, 1, 0, 0, 1, None) == -1   # interleaved layout: n <= 8
     assert L.lu_batched_inplace(None, None, 4, 1, 0, 2) == -3     # dtype
     assert L.lu_batched_inplace(None, None, 4, -1, 0, 0) == -4    # batch
     assert b"batch" in L.lu_batched_last_error()
@@ -68,7 +71,7 @@ def test_argument_errors_are_codes_not_exits():
     with pytest.raises(lub.LubError):
         lub.lu_batched_inplace(np.zeros((2, 3, 3), np.int32))
     with pytest.raises(lub.LubError):
-        lub.lu_batched_inplace(np.zeros((2, 3, 3), np.float32), pivot_mode="lapack")
+        lub.lu_batched_inplace(np.zeros((2, 3, 3), np.float32), pivot_mode="no such mode")
 
 
 @pytest.mark.skipif(HAVE_CUDA, reason="box has a GPU")
@@ -213,3 +216,20 @@ def test_shard_range_partitions_the_batch():
             assert spans[0][0] == 0 and spans[-1][1] == batch
             assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
             assert max(hi - lo for lo, hi in spans) <= -(-batch // world)
+
+
+def test_ipiv_to_perm_host_helper():
+    """LAPACK swap lists -> permutation vectors (lu_batched_ipiv_to_perm), against a literal replay."""
+    rng = np.random.default_rng(3)
+    n, b = 11, 50
+    ipiv = np.stack([np.array([rng.integers(k, n) + 1 for k in range(n)], np.int32) for _ in range(b)])
+    perm = lub.ipiv_to_perm(ipiv)
+    for i in range(b):
+        p = list(range(n))
+        for k in range(n):
+            q = ipiv[i, k] - 1
+            p[k], p[q] = p[q], p[k]
+        assert perm[i].tolist() == p
+    bad = ipiv.copy(); bad[0, 3] = 2            # points above the diagonal: not a getrf swap list
+    with pytest.raises(lub.LubError):
+        lub.ipiv_to_perm(bad)
