@@ -118,6 +118,22 @@ int lu_batched_set_stream(void* stream);
 int lu_batched_inplace_host(void* host_ptr, int32_t* host_piv, int n, int64_t batch, int pivot_mode,
                             int dtype);
 
+/* The same over SEVERAL devices of this process (contiguous shards, no exchange): device d of
+ * n_devices (0 = all visible) takes matrices [d * ceil(batch / n_devices), ...), one host thread and one pipeline per
+ * device.  This is what a C caller replacing main()'s single-GPU sequence (parallel_pivot/luBatchedInplace.cu:112-135)
+ * calls to use the whole box.  flags:
+ *   LUB_HOST_REGISTER      page-lock the caller's (pageable) buffers in place for the duration of the call, so the
+ *                          copies run as DMA at full speed (a pinned buffer is left alone);
+ *   LUB_HOST_BIND_THREADS  bind every worker to the CPUs next to its GPU (/sys/bus/pci/devices/<id>/local_cpulist).
+ * Where the host buffer physically lives decides the ceiling (a buffer on one NUMA node feeds every GPU through that
+ * node's memory controllers): lu_batched_bind_thread_near_device binds the CALLING thread next to a device, for
+ * callers that allocate (first touch) their buffers per device. */
+#define LUB_HOST_REGISTER 1
+#define LUB_HOST_BIND_THREADS 2
+int lu_batched_inplace_host_multi(void* host_ptr, int32_t* host_piv, int n, int64_t batch, int pivot_mode,
+                                  int dtype, int n_devices, int flags);
+int lu_batched_bind_thread_near_device(int device);
+
 /* NUMTHREADS knob (templated/luBatchedInplace.cu:6; table templated/run.py:201-223):
  * threads per block for subsequent launches of the calling thread, a multiple of 32 in [32, 256];
  * 0 restores the library's per-(n, dtype, pivot_mode) default.  lu_batched_get_threads returns the

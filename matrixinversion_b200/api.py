@@ -145,6 +145,31 @@ def lu_batched_inplace(A, piv=None, pivot_mode="parallel", stream=None, info=Non
     return A
 
 
+def lu_batched_inplace_host_multi(A: np.ndarray, piv=None, pivot_mode="parallel", n_devices: int = 0, register: bool = False,
+                                  bind_threads: bool = True) -> np.ndarray:
+    """lu_batched_inplace_host_multi: the host-buffer call over several GPUs of this process (contiguous shards, one
+    worker thread + pipeline per device).  A: writable C-contiguous numpy [batch, n, n]; n_devices 0 =
+    all visible.  register: page-lock a pageable buffer for the call; bind_threads: workers run next to their GPU."""
+    L = _lib.lib()
+    batch, n = _check_batch(A.shape)
+    if not isinstance(A, np.ndarray) or not A.flags.c_contiguous or not A.flags.writeable:
+        raise LubError(-4, "A must be a writable C-contiguous numpy array")
+    pptr = None
+    if piv is not None:
+        if not (isinstance(piv, np.ndarray) and piv.dtype == np.int32 and piv.shape == (batch, n) and piv.flags.c_contiguous):
+            raise LubError(-4, "piv must be a C-contiguous int32 [batch, n] numpy array")
+        pptr = piv.ctypes.data
+    flags = (_lib.HOST_REGISTER if register else 0) | (_lib.HOST_BIND_THREADS if bind_threads else 0)
+    check(L.lu_batched_inplace_host_multi(A.ctypes.data, pptr, n, batch, _mode(pivot_mode), _dtype_code(A.dtype), int(n_devices), flags))
+    return A
+
+
+def bind_thread_near_device(device: int) -> bool:
+    """Bind the calling thread to the CPUs next to a GPU (lu_batched_bind_thread_near_device), e.g. before allocating the
+    host buffers that will feed it (first touch places them on that NUMA node).  False when the topology is not exposed."""
+    return _lib.lib().lu_batched_bind_thread_near_device(int(device)) == 0
+
+
 def ipiv_to_perm(ipiv: np.ndarray) -> np.ndarray:
     """LAPACK swap lists (pivot_mode "lapack": 1-based ipiv[batch, n]) -> the permutation vectors the other modes
     write to piv (row i of P A is row perm[i] of A), e.g. for verify_lu."""

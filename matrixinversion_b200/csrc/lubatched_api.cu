@@ -13,6 +13,11 @@
 #include <iostream>
 #include <string>
 #include <vector>
+#include <cctype>
+#include <mutex>
+#include <thread>
+#include <pthread.h>
+#include <sched.h>
 
 #include "../../include/lubatched.h"
 #include "lub_launch.cuh"
@@ -234,26 +239,97 @@ __global__ void verify_kernel(const T* __restrict__ A, const T* __restrict__ X, 
     }
 }
 
-// ---- scratch buffers for the host-pointer pipeline ----------------------------------------
+// ---- the host-pointer pipeline -------------------------------------------------------------
 
+// Device-side staging of one device: three chunk buffers on three streams (H2D / kernel / D2H of consecutive chunks
+// overlap).  One per device, created on first use, serialised by its mutex (two host threads may target one GPU).
 struct HostPipe {
     static constexpr int kSlots = 3;
+    std::mutex mu;
     void* buf[kSlots] = {nullptr, nullptr, nullptr};
     int32_t* pbuf[kSlots] = {nullptr, nullptr, nullptr};
     size_t cap = 0, pcap = 0;
     cudaStream_t st[kSlots] = {nullptr, nullptr, nullptr};
-    int dev = -1;
-    void release() {
-        for (int i = 0; i < kSlots; ++i) {
-            if (buf[i]) cudaFree(buf[i]);
-            if (pbuf[i]) cudaFree(pbuf[i]);
-            if (st[i]) cudaStreamDestroy(st[i]);
-            buf[i] = nullptr; pbuf[i] = nullptr; st[i] = nullptr;
-        }
-        cap = pcap = 0; dev = -1;
-    }
 };
-thread_local HostPipe g_pipe;
+HostPipe g_pipes[lub::kMaxDevices];
+
+unsigned long long host_chunk_mib() {  // tuning knob, default 64 MiB (profiles/r01_tune_v6.md section 4)
+    static const unsigned long long v = []() -> unsigned long long {
+        const char* e = std::getenv("LUB_HOST_CHUNK_MIB");
+        const long x = e ? std::atol(e) : 0;
+        return (x >= 1 && x <= 4096) ? (unsigned long long)x : 64ull;
+    }();
+    return v;
+}
+
+// main()'s cudaMalloc + H2D + launch + D2H (parallel_pivot/luBatchedInplace.cu:112-135) for `batch` matrices that start
+// at host_ptr, on the CURRENT device, chunked and pipelined.  Synchronous.
+int host_pipeline(void* host_ptr, int32_t* host_piv, int n, int64_t batch, int mode, int dtype) {
+    if (batch == 0) return LUB_OK;
+    const size_t mat_bytes = (size_t)n * n * esize(dtype);
+    // ~64 MiB chunks, a whole number of matrices, at least 3 chunks in flight when possible
+    int64_t chunk = std::max<int64_t>(1, (int64_t)((host_chunk_mib() << 20) / mat_bytes));
+    chunk = std::min<int64_t>(chunk, std::max<int64_t>(1, (batch + HostPipe::kSlots - 1) / HostPipe::kSlots));
+    int dev = 0;
+    CU(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= lub::kMaxDevices) return fail(LUB_ERR_CUDA, "device index out of range");
+    HostPipe& P = g_pipes[dev];
+    std::lock_guard<std::mutex> lk(P.mu);
+    const size_t need = (size_t)chunk * mat_bytes, pneed = host_piv ? (size_t)chunk * n * 4 : 0;
+    for (int i = 0; i < HostPipe::kSlots; ++i) {
+        if (!P.st[i]) CU(cudaStreamCreateWithFlags(&P.st[i], cudaStreamNonBlocking));
+        if (P.cap < need) { if (P.buf[i]) cudaFree(P.buf[i]); P.buf[i] = nullptr; CU(cudaMalloc(&P.buf[i], need)); }
+        if (P.pcap < pneed) { if (P.pbuf[i]) cudaFree(P.pbuf[i]); P.pbuf[i] = nullptr; CU(cudaMalloc((void**)&P.pbuf[i], pneed)); }
+    }
+    P.cap = std::max(P.cap, need);
+    P.pcap = std::max(P.pcap, pneed);
+    char* h = static_cast<char*>(host_ptr);
+    int slot = 0, rc = LUB_OK;
+    for (int64_t b0 = 0; b0 < batch && rc == LUB_OK; b0 += chunk, slot = (slot + 1) % HostPipe::kSlots) {
+        const int64_t nb = std::min<int64_t>(chunk, batch - b0);
+        cudaStream_t s = P.st[slot];
+        cudaError_t e = cudaMemcpyAsync(P.buf[slot], h + (size_t)b0 * mat_bytes, (size_t)nb * mat_bytes, cudaMemcpyHostToDevice, s);
+        if (e != cudaSuccess) { rc = cuda_fail(e, "cudaMemcpyAsync(H2D)"); break; }
+        rc = launch_on(P.buf[slot], host_piv ? P.pbuf[slot] : nullptr, n, nb, mode, dtype, s, nullptr, 0);
+        if (rc != LUB_OK) break;
+        e = cudaMemcpyAsync(h + (size_t)b0 * mat_bytes, P.buf[slot], (size_t)nb * mat_bytes, cudaMemcpyDeviceToHost, s);
+        if (e == cudaSuccess && host_piv) e = cudaMemcpyAsync(host_piv + b0 * n, P.pbuf[slot], (size_t)nb * n * 4, cudaMemcpyDeviceToHost, s);
+        if (e != cudaSuccess) rc = cuda_fail(e, "cudaMemcpyAsync(D2H)");
+    }
+    // also on an error: copies already queued still read / write the caller's buffer, drain them first
+    for (int i = 0; i < HostPipe::kSlots; ++i) {
+        const cudaError_t e = cudaStreamSynchronize(P.st[i]);
+        if (e != cudaSuccess && rc == LUB_OK) rc = cuda_fail(e, "cudaStreamSynchronize");
+    }
+    return rc;
+}
+
+// CPUs next to a GPU: /sys/bus/pci/devices/<bus id>/local_cpulist ("0-31,64-95").  Empty set when unknown.
+bool device_local_cpus(int dev, cpu_set_t* set) {
+    CPU_ZERO(set);
+    char bus[32] = {0};
+    if (cudaDeviceGetPCIBusId(bus, sizeof(bus), dev) != cudaSuccess) return false;
+    for (char* c = bus; *c; ++c) *c = (char)std::tolower((unsigned char)*c);
+    std::ifstream f(std::string("/sys/bus/pci/devices/") + bus + "/local_cpulist");
+    std::string list;
+    if (!f || !std::getline(f, list)) return false;
+    int count = 0;
+    size_t i = 0;
+    while (i < list.size()) {
+        char* end = nullptr;
+        const long a = std::strtol(list.c_str() + i, &end, 10);
+        if (end == list.c_str() + i) break;
+        long b = a;
+        i = (size_t)(end - list.c_str());
+        if (i < list.size() && list[i] == '-') {
+            b = std::strtol(list.c_str() + i + 1, &end, 10);
+            i = (size_t)(end - list.c_str());
+        }
+        for (long c = a; c <= b && c < CPU_SETSIZE; ++c) { CPU_SET((int)c, set); ++count; }
+        if (i < list.size() && list[i] == ',') ++i;
+    }
+    return count > 0;
+}
 
 }  // namespace
 
@@ -374,43 +450,64 @@ int lu_batched_inplace_host(void* host_ptr, int32_t* host_piv, int n, int64_t ba
     if (rc != LUB_OK) return rc;
     if (batch == 0) return LUB_OK;
     if (!host_ptr) return fail(LUB_ERR_BAD_ARG, "host_ptr is NULL");
+    return host_pipeline(host_ptr, host_piv, n, batch, pivot_mode, dtype);
+}
+
+int lu_batched_bind_thread_near_device(int device) {
+    int count = 0;
+    CU(cudaGetDeviceCount(&count));
+    if (device < 0 || device >= count) return fail(LUB_ERR_BAD_ARG, "no such device");
+    cpu_set_t set;
+    if (!device_local_cpus(device, &set)) return fail(LUB_ERR_IO, "the PCI topology of the device is not exposed in /sys");
+    if (sched_setaffinity(0, sizeof(set), &set) != 0) return fail(LUB_ERR_IO, "sched_setaffinity failed");
+    return LUB_OK;
+}
+
+int lu_batched_inplace_host_multi(void* host_ptr, int32_t* host_piv, int n, int64_t batch, int pivot_mode, int dtype,
+                                  int n_devices, int flags) {
+    int rc = check_args(n, batch, pivot_mode, dtype);
+    if (rc != LUB_OK) return rc;
+    int count = 0;
+    CU(cudaGetDeviceCount(&count));
+    if (n_devices <= 0) n_devices = count;
+    if (n_devices > count || n_devices > lub::kMaxDevices) return fail(LUB_ERR_BAD_ARG, "n_devices exceeds the devices visible to this process");
+    if (batch == 0) return LUB_OK;
+    if (!host_ptr) return fail(LUB_ERR_BAD_ARG, "host_ptr is NULL");
     const size_t mat_bytes = (size_t)n * n * esize(dtype);
-    // ~64 MiB chunks, a whole number of matrices, at least 3 chunks in flight when possible
-    static const unsigned long long chunk_mib = []() -> unsigned long long {  // tuning knob, default 64 MiB
-        const char* e = std::getenv("LUB_HOST_CHUNK_MIB");
-        const long v = e ? std::atol(e) : 0;
-        return (v >= 1 && v <= 4096) ? (unsigned long long)v : 64ull;
-    }();
-    int64_t chunk = std::max<int64_t>(1, (int64_t)((chunk_mib << 20) / mat_bytes));
-    chunk = std::min<int64_t>(chunk, std::max<int64_t>(1, (batch + HostPipe::kSlots - 1) / HostPipe::kSlots));
-    int dev = 0;
-    CU(cudaGetDevice(&dev));
-    HostPipe& P = g_pipe;
-    if (P.dev != dev) P.release();
-    P.dev = dev;
-    const size_t need = (size_t)chunk * mat_bytes, pneed = host_piv ? (size_t)chunk * n * 4 : 0;
-    for (int i = 0; i < HostPipe::kSlots; ++i) {
-        if (!P.st[i]) CU(cudaStreamCreateWithFlags(&P.st[i], cudaStreamNonBlocking));
-        if (P.cap < need) { if (P.buf[i]) cudaFree(P.buf[i]); P.buf[i] = nullptr; CU(cudaMalloc(&P.buf[i], need)); }
-        if (P.pcap < pneed) { if (P.pbuf[i]) cudaFree(P.pbuf[i]); P.pbuf[i] = nullptr; CU(cudaMalloc((void**)&P.pbuf[i], pneed)); }
+    bool reg_a = false, reg_p = false;
+    if (flags & LUB_HOST_REGISTER) {  // page-lock the caller's pageable buffers in place for the duration of the call
+        reg_a = cudaHostRegister(host_ptr, (size_t)batch * mat_bytes, cudaHostRegisterPortable) == cudaSuccess;
+        if (host_piv) reg_p = cudaHostRegister(host_piv, (size_t)batch * n * 4, cudaHostRegisterPortable) == cudaSuccess;
+        cudaGetLastError();  // "already registered" / pinned by the caller is fine
     }
-    P.cap = std::max(P.cap, need);
-    P.pcap = std::max(P.pcap, pneed);
-    char* h = static_cast<char*>(host_ptr);
-    int slot = 0;
-    for (int64_t b0 = 0; b0 < batch; b0 += chunk, slot = (slot + 1) % HostPipe::kSlots) {
-        const int64_t nb = std::min<int64_t>(chunk, batch - b0);
-        cudaStream_t s = P.st[slot];
-        CU(cudaMemcpyAsync(P.buf[slot], h + (size_t)b0 * mat_bytes, (size_t)nb * mat_bytes, cudaMemcpyHostToDevice, s));
-        rc = launch_on(P.buf[slot], host_piv ? P.pbuf[slot] : nullptr, n, nb, pivot_mode, dtype, s, nullptr, 0);
-        if (rc != LUB_OK) {  // copies already queued still read / write the caller's buffer: drain them first
-            for (int i = 0; i < HostPipe::kSlots; ++i) cudaStreamSynchronize(P.st[i]);
-            return rc;
-        }
-        CU(cudaMemcpyAsync(h + (size_t)b0 * mat_bytes, P.buf[slot], (size_t)nb * mat_bytes, cudaMemcpyDeviceToHost, s));
-        if (host_piv) CU(cudaMemcpyAsync(host_piv + b0 * n, P.pbuf[slot], (size_t)nb * n * 4, cudaMemcpyDeviceToHost, s));
+    int dev0 = 0;
+    cudaGetDevice(&dev0);
+    const int knob = g_threads;
+    const int64_t per = (batch + n_devices - 1) / n_devices;   // contiguous shards, SURVEY.md 8(e)
+    std::vector<int> rcs(n_devices, LUB_OK);
+    std::vector<std::string> errs(n_devices);
+    std::vector<std::thread> workers;
+    for (int d = 0; d < n_devices; ++d) {
+        workers.emplace_back([&, d]() {
+            const int64_t lo = std::min<int64_t>(batch, d * per), hi = std::min<int64_t>(batch, lo + per);
+            if (hi <= lo) return;
+            if (cudaSetDevice(d) != cudaSuccess) { rcs[d] = LUB_ERR_CUDA; errs[d] = "cudaSetDevice failed"; return; }
+            if (flags & LUB_HOST_BIND_THREADS) {
+                cpu_set_t set;
+                if (device_local_cpus(d, &set)) pthread_setaffinity_np(pthread_self(), sizeof(set), &set);
+            }
+            g_threads = knob;
+            rcs[d] = host_pipeline(static_cast<char*>(host_ptr) + (size_t)lo * mat_bytes, host_piv ? host_piv + lo * n : nullptr, n, hi - lo,
+                                   pivot_mode, dtype);
+            if (rcs[d] != LUB_OK) errs[d] = g_err;
+        });
     }
-    for (int i = 0; i < HostPipe::kSlots; ++i) CU(cudaStreamSynchronize(P.st[i]));
+    for (auto& w : workers) w.join();
+    cudaSetDevice(dev0);
+    if (reg_a) cudaHostUnregister(host_ptr);
+    if (reg_p) cudaHostUnregister(host_piv);
+    for (int d = 0; d < n_devices; ++d)
+        if (rcs[d] != LUB_OK) return fail(rcs[d], "device " + std::to_string(d) + ": " + errs[d]);
     return LUB_OK;
 }
 

@@ -143,3 +143,25 @@ def test_interleaved_layout_is_bitwise_equal_to_matrix_major(dtype):
     assert torch.equal(view.permute(2, 0, 1).contiguous(), ref) and flat[0].item() == 0.0
     with pytest.raises(lub.LubError):
         lub.lu_batched_inplace(torch.zeros((9, 9, 64), device="cuda"), None, "none", layout="interleaved")
+
+
+def test_host_multi_device_entry_point_equals_the_single_device_path():
+    """lu_batched_inplace_host_multi: contiguous shards over every visible GPU (one on a single-GPU box), pageable
+    buffer registered for the call, workers bound next to their GPU -- bitwise the results of the device-pointer path."""
+    ndev = torch.cuda.device_count()
+    for n, dtype, mode in ((32, np.float32, "parallel"), (18, np.float32, "parallel"), (7, np.float64, "serial"), (32, np.float64, "lapack")):
+        A = synthetic(n, 4099, dtype)                       # odd batch: ragged shards and tiles
+        dA = torch.from_numpy(A).cuda()
+        piv = torch.zeros((4099, n), dtype=torch.int32, device="cuda")
+        lub.lu_batched_inplace(dA, piv, mode)
+        torch.cuda.synchronize()
+        want, want_piv = dA.cpu().numpy(), piv.cpu().numpy()
+        for nd in sorted({1, ndev, 0}):
+            for register in (False, True):
+                H = A.copy()
+                hp = np.full((4099, n), -3, np.int32)
+                lub.lu_batched_inplace_host_multi(H, hp, mode, n_devices=nd, register=register)
+                assert np.array_equal(H, want, equal_nan=True) and np.array_equal(hp, want_piv), (n, mode, nd, register)
+    with pytest.raises(lub.LubError):
+        lub.lu_batched_inplace_host_multi(np.zeros((4, 3, 3), np.float32), n_devices=ndev + 1)
+    assert lub.bind_thread_near_device(0) in (True, False)
