@@ -4,6 +4,7 @@
 #include <cstdio>
 #include "lub_v5.cuh"
 #include "lub_tma2.cuh"
+#include "../../matrixinversion_b200/csrc/lub_dmma.cuh"
 #include "lub_v6.cuh"
 
 using namespace lub;
@@ -113,6 +114,27 @@ struct VT2 {
     static Variant make(const char* name) { return Variant{name, L::MPW, -1000000, MAXT, set_attr, launch, occ, &smem_of}; }
 };
 #define VART2(N, GR, GC, MODE, MAXT, K1) VT2<N, GR, GC, MODE, MAXT, K1>::make("float N=" #N " " #GR "x" #GC " mode" #MODE " maxt" #MAXT " k1_" #K1 " tma2")
+
+// fp64 N = 32 DMMA kernel (lub_dmma.cuh)
+template <int MODE, int MINB, int BS>
+struct VDM {
+    using L = TmaLayout<double, 32, 8, 4, MODE>;
+    static constexpr auto kern() { return lub_dmma_kernel<MODE, MINB, (BS & 1) != 0>; }
+    static void set_attr(int smem) { cudaFuncSetAttribute(kern(), cudaFuncAttributeMaxDynamicSharedMemorySize, smem); }
+    static void launch(void* A, int* piv, long long batch, unsigned blocks, int threads, int smem, cudaStream_t s) {
+        CUtensorMap map;
+        if (make_batch_tmap<double>(&map, A, 32, batch, L::MPW) != cudaSuccess) { printf("tensor map failed\n"); return; }
+        kern()<<<blocks, threads, smem, s>>>(map, (double*)A, piv, batch);
+    }
+    static int occ(int threads, int smem) {
+        int o = 0;
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, kern(), threads, smem);
+        return o;
+    }
+    static int smem_of(int warps) { return L::smem_bytes(warps, 1); }
+    static Variant make(const char* name) { return Variant{name, L::MPW, -1000000, 256, set_attr, launch, occ, &smem_of}; }
+};
+#define VARDM(MODE, MINB, BS) VDM<MODE, MINB, BS>::make("double N=32 8x4 mode" #MODE " minb" #MINB " bs" #BS " dmma")
 
 // warp-specialised TMA kernel: one persistent block per SM; warp_bytes == -2000000 marks it
 template <typename T, int N, int GR, int GC, int MODE, int NCW, int NPW, int NB, int CREG, int PREG, int NCG, int LA, int DBG>
