@@ -14,14 +14,15 @@
 //
 // One block step eliminates the four pivots K = 4kb .. 4kb + 3 at once (same pivots, in the same order, as four
 // unblocked steps -- the row permutation was applied on the way in, exactly as in the other kernels):
-//     P    = inv(A[K][K])                   4 x 4 Gauss-Jordan on 16 lanes (one element per lane, 12 shuffles)
+//     P    = inv(A[K][K])                   4 x 4 Gauss-Jordan on 16 lanes (one element per lane, 12 64-bit shuffles)
 //     C'   = A[:][K] * P                    4 DMMA   (new columns K are -C', and -C' is the A operand of the update)
-//     R'   = P * A[K][:]                    4 DMMA   (new rows K)
-//     A   += (-C') * A[K][:]               16 DMMA   (rank-4 update of the whole matrix; rows / columns K are
-//                                                     overwritten afterwards with R', -C' and P)
-// The only cross-lane traffic is the conversion of the row panel into B fragments and of the column panel (twice)
-// into A fragments: 41 64-bit shuffles per block step against 104 32-bit... = 82 against 104 32-bit shuffles for the
-// four unblocked steps, and 24 tensor instructions against 128 DFMA.
+//     A   += [-C' ; P - I] * A[K][:]       16 DMMA   (rank-4 update of the whole matrix; on the rows of K the A operand is
+//                                                     P - I, which turns them into P * A[K][:]; columns K are overwritten
+//                                                     afterwards with -C' and P)
+// The panels travel through a 2.3 KB per-warp scratch in their natural layout (owners store 16-byte pairs, everybody
+// loads its one fragment element per tile): 12 STS.128 + 15 LDS per block step, no selects -- the first version,
+// which converted accumulator <-> fragment layouts with shuffles (41 64-bit shuffles + as many selects per block
+// step), ran 3406 instructions per matrix and was no faster than the DFMA kernel (6.58 vs 6.33 ms).
 #pragma once
 #include "lub_tma.cuh"
 
@@ -32,92 +33,95 @@ __device__ __forceinline__ void dmma8x8x4(double& d0, double& d1, double a, doub
 }
 __device__ __forceinline__ double shfl_d(double v, int src) { return __shfl_sync(0xffffffffu, v, src); }
 
-// c[I][J][s]: element (8I + g, 8J + 2t + s) of the (row-permuted) matrix; on return the inverse.
-__device__ __forceinline__ void gj_eliminate_dmma32(double (&c)[4][4][2], int lane) {
-    const int g = lane >> 2, t = lane & 3;
+// 1 / x without the IEEE division's special-case branches: MUFU.RCP64H seed + two Newton steps (<= 1 ulp for normal x;
+// a zero pivot still gives inf / NaN, like the division in the other fp64 kernels -- SURVEY.md Q7)
+__device__ __forceinline__ double rcp_fast(double x) {
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    r = fma(fma(-x, r, 1.0), r, r);
+    r = fma(fma(-x, r, 1.0), r, r);
+    return r;
+}
+
+// per-warp scratch for the panels of one block step (doubles): row panel 4 x 32 (row pitch 36: conflict-free fragment
+// reads), column panel 32 x 4, the 4 x 4 block
+struct DmmaScratch {
+    static constexpr int RP = 36;
+    static constexpr int kRow = 0, kCol = 4 * RP, kP = 4 * RP + 128, kDoubles = 4 * RP + 128 + 16;
+    static constexpr int BYTES = ((kDoubles * 8 + 15) / 16) * 16;
+};
+
+// c[I][J][s]: element (8I + g, 8J + 2t + s) of the (row-permuted) matrix; on return the inverse.  `sc`: this warp's scratch.
+__device__ __forceinline__ void gj_eliminate_dmma32(double (&c)[4][4][2], double* __restrict__ sc, int lane) {
+    const int g = lane >> 2, t = lane & 3, gi = g & 3;
+    double* Rp = sc + DmmaScratch::kRow;
+    double* Cp = sc + DmmaScratch::kCol;
+    double* Ps = sc + DmmaScratch::kP;
+    const int base16 = (g & 4) << 2;                                   // first lane of this lane's group of 16
+    const double* rp_rd = Rp + t * DmmaScratch::RP + g;                 // B fragment: Rp[t][8J + g]
+    const double* cp_rd = Cp + (g << 2) + t;                            // A fragment: Cp[8I + g][t]
 #pragma unroll
     for (int kb = 0; kb < 8; ++kb) {
         const int Ik = kb >> 1, h = kb & 1;        // the tile row / column holding K, and which half of it
         const bool rowK = (g >> 2) == h;           // this lane owns rows of K (in tile row Ik)
         const bool colK = (t >> 1) == h;           // this lane owns columns of K (in tile column Ik)
-        const int gi = g & 3;
-        // ---- P0 = A[K][K] on 16 lanes: lane (4h + i, t) <- A[4kb + i][4kb + t] ----
-        double p;
-        {
-            const int src = ((4 * h + gi) << 2) + 2 * h + (t >> 1);
-            const double x0 = shfl_d(c[Ik][Ik][0], src), x1 = shfl_d(c[Ik][Ik][1], src);
-            p = (t & 1) ? x1 : x0;
+        // ---- the two panels -> scratch, in natural layout (owners only) ----
+        __syncwarp();
+        if (rowK) {
+#pragma unroll
+            for (int J = 0; J < 4; ++J) st_vec<double, 2>(Rp + gi * DmmaScratch::RP + 8 * J + 2 * t, c[Ik][J]);
         }
-        // ---- P = inv(P0): Gauss-Jordan on the 4 x 4 block, row gi / column t of every quad-group of 16 lanes ----
+        if (colK) {
+#pragma unroll
+            for (int I = 0; I < 4; ++I) st_vec<double, 2>(Cp + ((8 * I + g) << 2) + 2 * (t & 1), c[I][Ik]);
+        }
+        __syncwarp();
+        // ---- P = inv(A[K][K]): Gauss-Jordan on the 4 x 4 block, one element per lane in each group of 16 lanes ----
+        double p = Rp[gi * DmmaScratch::RP + 4 * kb + t];
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-            const int base = (g & 4) << 2;                       // first lane of this lane's group of 16
-            const double pv = shfl_d(p, base + (k << 2) + k);
-            const double rk = shfl_d(p, base + (k << 2) + t);     // pivot row, my column
-            const double ck = shfl_d(p, base + (gi << 2) + k);    // my row, pivot column
-            const double rinv = 1.0 / pv;
-            const double rs = (t == k) ? rinv : rk * rinv;       // scaled pivot row (1/pivot in the pivot column)
+            const double pv = shfl_d(p, base16 + (k << 2) + k);
+            const double rk = shfl_d(p, base16 + (k << 2) + t);     // pivot row, my column
+            const double ck = shfl_d(p, base16 + (gi << 2) + k);    // my row, pivot column
+            const double rinv = rcp_fast(pv);
+            const double rs = (t == k) ? rinv : rk * rinv;         // scaled pivot row (1/pivot in the pivot column)
             const double upd = (t == k) ? -(ck * rinv) : fma(-ck, rs, p);
             p = (gi == k) ? rs : upd;
         }
-        // P[i][j] now sits in lane (4h' + i, j) of BOTH halves h' (each half inverted what it fetched; they fetched the same)
-        const double aP = rowK ? p : 0.0;                                        // A fragment: rows 4h + i = P[i][:]
-        const double pT = shfl_d(p, ((g & 4) << 2) + (t << 2) + gi);             // lane (., i, j) <- P[j][i]
-        const double bP = rowK ? pT : 0.0;                                       // B fragment: B[k = t][n = 4h + j] = P[t][j]
-        // ---- row panel A[K][:] as B fragments: B_J[k = t][n = g] = A[4kb + t][8J + g] ----
-        double bR[4];
-        {
-            const int src = ((4 * h + t) << 2) + (g >> 1);
+        if (g < 4) Ps[(gi << 2) + t] = p;                           // P[i][j] (both groups of 16 hold the same P)
+        // ---- fragments of the raw panels ----
+        double bR[4], aC[4];
 #pragma unroll
-            for (int J = 0; J < 4; ++J) {
-                const double x0 = shfl_d(c[Ik][J][0], src), x1 = shfl_d(c[Ik][J][1], src);
-                bR[J] = (g & 1) ? x1 : x0;
-            }
-        }
-        // ---- column panel A[:][K] as A fragments: A_I[m = g][k = t] = A[8I + g][4kb + t] ----
-        double aC[4];
-        {
-            const int src = (g << 2) + 2 * h + (t >> 1);
+        for (int J = 0; J < 4; ++J) bR[J] = rp_rd[8 * J];
 #pragma unroll
-            for (int I = 0; I < 4; ++I) {
-                const double y0 = shfl_d(c[I][Ik][0], src), y1 = shfl_d(c[I][Ik][1], src);
-                aC[I] = (t & 1) ? y1 : y0;
-            }
-        }
-        // ---- C' = A[:][K] * P (lands in the C-layout positions of columns K), R' = P * A[K][:] (in rows K) ----
-        double d1[4][2], d2[4][2];
+        for (int I = 0; I < 4; ++I) aC[I] = cp_rd[32 * I];
+        __syncwarp();
+        // A fragment of (P - I) on rows K (folded into the update of tile row Ik: rows K become P * A[K][:]);
+        // B fragment of P on columns K (C' = A[:][K] * P lands in the C-layout positions of columns K)
+        const double pT = Ps[(t << 2) + gi];                        // P[t][gi]
+        const double aPI = rowK ? (p - ((gi == t) ? 1.0 : 0.0)) : 0.0;
+        const double bP = rowK ? pT : 0.0;
+        double pc[2];                                               // P in the C layout: (4h + i, 4h + 2(t & 1) + s)
+        ld_vec<double, 2>(Ps + (gi << 2) + 2 * (t & 1), pc);
+        double d1[4][2];
 #pragma unroll
         for (int I = 0; I < 4; ++I) { d1[I][0] = 0.0; d1[I][1] = 0.0; dmma8x8x4(d1[I][0], d1[I][1], aC[I], bP); }
+        // ---- -C' as A fragments, through the column-panel scratch ----
+        if (colK) {
 #pragma unroll
-        for (int J = 0; J < 4; ++J) { d2[J][0] = 0.0; d2[J][1] = 0.0; dmma8x8x4(d2[J][0], d2[J][1], aP, bR[J]); }
-        // ---- -C' as A fragments (rows of K excluded: they are replaced, not updated) ----
-        double aN[4];
-        {
-            const int src = (g << 2) + 2 * h + (t >> 1);
-#pragma unroll
-            for (int I = 0; I < 4; ++I) {
-                const double y0 = shfl_d(d1[I][0], src), y1 = shfl_d(d1[I][1], src);
-                aN[I] = -((t & 1) ? y1 : y0);
-            }
-            aN[Ik] = rowK ? 0.0 : aN[Ik];
+            for (int I = 0; I < 4; ++I) st_vec<double, 2>(Cp + ((8 * I + g) << 2) + 2 * (t & 1), d1[I]);
         }
+        __syncwarp();
+        double aN[4];
+#pragma unroll
+        for (int I = 0; I < 4; ++I) aN[I] = -cp_rd[32 * I];
+        aN[Ik] = rowK ? aPI : aN[Ik];               // rows K: += (P - I) * A[K][:] instead of -= C' * A[K][:]
         // ---- rank-4 update of the whole matrix ----
 #pragma unroll
         for (int I = 0; I < 4; ++I)
 #pragma unroll
             for (int J = 0; J < 4; ++J) dmma8x8x4(c[I][J][0], c[I][J][1], aN[I], bR[J]);
-        // ---- rows K <- R', columns K <- -C', block K x K <- P ----
-        double pc[2];  // P in the C layout: lane (4h + i, 2h + j / 2), slot j % 2 <- P[i][j]
-        {
-            const int base = (g & 4) << 2;
-            pc[0] = shfl_d(p, base + (gi << 2) + ((2 * (t & 1)) & 3));
-            pc[1] = shfl_d(p, base + (gi << 2) + ((2 * (t & 1) + 1) & 3));
-        }
-#pragma unroll
-        for (int J = 0; J < 4; ++J) {
-#pragma unroll
-            for (int s = 0; s < 2; ++s) c[Ik][J][s] = rowK ? d2[J][s] : c[Ik][J][s];
-        }
+        // ---- columns K <- -C', block K x K <- P ----
 #pragma unroll
         for (int I = 0; I < 4; ++I) {
 #pragma unroll
@@ -127,6 +131,10 @@ __device__ __forceinline__ void gj_eliminate_dmma32(double (&c)[4][4][2], int la
             }
         }
     }
+}
+
+constexpr int dmma_smem_bytes(int warps, int perm_bytes) {
+    return 1024 + warps * (32 * 256 + perm_bytes) + warps * 16 + 64 + warps * DmmaScratch::BYTES;
 }
 
 // One warp = one matrix (tile); persistent over tiles; TMA staging, pivot pre-pass, permuted register load, column
@@ -151,6 +159,8 @@ lub_dmma_kernel(const __grid_constant__ CUtensorMap tmap, double* __restrict__ A
     int* perm = reinterpret_cast<int*>(after + (size_t)warp * L::PERM_BYTES);
     unsigned long long* bar = reinterpret_cast<unsigned long long*>(after + (size_t)nwarps * L::PERM_BYTES) + 2 * warp;
     int8_t* slot_rank = reinterpret_cast<int8_t*>(after + (size_t)nwarps * L::PERM_BYTES + (size_t)nwarps * 16);
+    double* scratch = reinterpret_cast<double*>(after + (size_t)nwarps * L::PERM_BYTES + (size_t)nwarps * 16 + L::HEADER_BYTES) +
+                      (size_t)warp * (DmmaScratch::BYTES / 8);
 
     if (MODE == kModeParallel && threadIdx.x < N) slot_rank[threadIdx.x] = (int8_t)tree_slot_rank(threadIdx.x, N);
     if (lane == 0) mbar_init(bar, 1);
@@ -187,7 +197,7 @@ lub_dmma_kernel(const __grid_constant__ CUtensorMap tmap, double* __restrict__ A
             for (int J = 0; J < 4; ++J)
                 ld_vec<T, 2>(reinterpret_cast<const T*>(img + swz_byte<RB>(prow, (4 * J + t) << 4)), c[I][J]);
         }
-        gj_eliminate_dmma32(c, lane);
+        gj_eliminate_dmma32(c, scratch, lane);
         // ---- undo the row permutation as a column scatter (A^-1 = (P A)^-1 P); bulk tensor store ----
         __syncwarp();  // every lane holds its block: the image may be overwritten
         if (MODE == kModeNone) {

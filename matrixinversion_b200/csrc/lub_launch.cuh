@@ -12,6 +12,7 @@
 #include "lub_v3.cuh"
 #include "lub_v4.cuh"
 #include "lub_tma.cuh"
+#include "lub_dmma.cuh"
 
 namespace lub {
 
@@ -312,6 +313,26 @@ cudaError_t launch(void* A, int32_t* piv, long long batch, int threads_req, cuda
     static KernelCache cache_fast[kMaxDevices], cache_gen[kMaxDevices];
 
     using TC = TmaCfg<T, N, MODE>;
+    // fp64 N = 32 (BASELINE config 5): blocked Gauss-Jordan on the FP64 tensor cores (lub_dmma.cuh), four 128-thread
+    // blocks per SM: 6.31 -> 5.55 ms with pivoting, 6.45 -> 5.29 ms without (profiles/r02_dmma.md)
+    if constexpr (sizeof(T) == 8 && N == 32 && kUseTma) {
+        if (fast && batch <= 0x7fffff00ll) {
+            using TL = TmaLayout<T, N, 8, 4, MODE>;
+            auto kern = lub_dmma_kernel<MODE, 2, true>;
+            if (threads_req <= 0) x.threads = 128;
+            static KernelCache cache_dmma[kMaxDevices];
+            return run_kernel(kern, cache_dmma[dev], x, kMaxThreads, [](int w) { return dmma_smem_bytes(w, TL::PERM_BYTES); }, TL::MPW, TL::G,
+                              "lub_dmma_kernel", [&](unsigned blocks, int smem) {
+                                  const CUtensorMap* map = nullptr;
+                                  cudaError_t e = cached_batch_tmap<T>(&map, A, N, batch, TL::MPW, dev);
+                                  if (e != cudaSuccess) return e;
+                                  e = start();
+                                  if (e != cudaSuccess) return e;
+                                  kern<<<blocks, x.threads, smem, stream>>>(*map, At, piv, batch);
+                                  return cudaGetLastError();
+                              });
+        }
+    }
     // TMA tile coordinates are 32-bit: larger batches take the v3 / v4 kernels (64-bit index arithmetic)
     if constexpr (TC::ON) {
         if (fast && batch <= 0x7fffff00ll) {

@@ -131,7 +131,7 @@ struct VDM {
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, kern(), threads, smem);
         return o;
     }
-    static int smem_of(int warps) { return L::smem_bytes(warps, 1); }
+    static int smem_of(int warps) { return dmma_smem_bytes(warps, L::PERM_BYTES); }
     static Variant make(const char* name) { return Variant{name, L::MPW, -1000000, 256, set_attr, launch, occ, &smem_of}; }
 };
 #define VARDM(MODE, MINB, BS) VDM<MODE, MINB, BS>::make("double N=32 8x4 mode" #MODE " minb" #MINB " bs" #BS " dmma")
