@@ -377,8 +377,13 @@ cudaError_t launch(void* A, int32_t* piv, long long batch, int threads_req, cuda
     constexpr bool V3_PF = !USE_V4 && (MODE == kModeNone) && V3Layout<T, N, VC::GR, VC::GC, MODE>::ROWVEC && N >= 12;
     constexpr bool V3_PFD = !USE_V4 && pick_pfd(N, (int)sizeof(T), MODE);
     constexpr bool V4_PFD = USE_V4 && pick_pfd64(N, MODE);
-    auto plain = [&](auto kern, int warp_bytes, const char* name) {
-        return run_kernel(kern, cf, x, kMaxThreads, [warp_bytes](int w) { return FL::HEADER_BYTES + w * warp_bytes; }, FL::MPW, FL::G, name,
+    // round 2 (profiles/r02_tune_v3.jsonl): the lean elimination step pays in lub_v3_kernel from N = 25 on (N = 31: -7..-9 % in
+    // every mode; N <= 28: +-0); without pivoting N = 30, 31 get the double-buffered prefetch they could not afford at two
+    // 256-thread blocks per SM (second image) by running one 384-thread block (N = 31: 3.14 -> 2.66 ms)
+    constexpr bool V3_LEAN = !USE_V4 && sizeof(T) == 4 && N >= 25;
+    constexpr bool V3_BIG = !USE_V4 && sizeof(T) == 4 && MODE == kModeNone && (N == 30 || N == 31);
+    auto plain = [&](auto kern, int warp_bytes, const char* name, int max_threads = kMaxThreads) {
+        return run_kernel(kern, cf, x, max_threads, [warp_bytes](int w) { return FL::HEADER_BYTES + w * warp_bytes; }, FL::MPW, FL::G, name,
                           [&](unsigned blocks, int smem) {
                               cudaError_t e = start();
                               if (e != cudaSuccess) return e;
@@ -386,16 +391,19 @@ cudaError_t launch(void* A, int32_t* piv, long long batch, int threads_req, cuda
                               return cudaGetLastError();
                           });
     };
-    if constexpr (V3_PFD)
-        return plain(lub_v3_kernel<T, N, VC::GR, VC::GC, MODE, VC::MINB, VC::BSYNC, false, true>, FL::WARP_BYTES_PFD, "lub_v3_kernel");
+    if constexpr (V3_BIG) {
+        if (threads_req <= 0) x.threads = 384;
+        return plain(lub_v3_kernel<T, N, VC::GR, VC::GC, MODE, 1, false, false, true, true, 384>, FL::WARP_BYTES_PFD, "lub_v3_kernel", 384);
+    } else if constexpr (V3_PFD)
+        return plain(lub_v3_kernel<T, N, VC::GR, VC::GC, MODE, VC::MINB, VC::BSYNC, false, true, V3_LEAN>, FL::WARP_BYTES_PFD, "lub_v3_kernel");
     else if constexpr (USE_V4 && V4_PFD)
         return plain(lub_v4_kernel<T, N, VC::GR, VC::GC, MODE, VC::MINB, false, true>, FL::WARP_BYTES_PFD, "lub_v4_kernel");
     else if constexpr (USE_V4)
         return plain(lub_v4_kernel<T, N, VC::GR, VC::GC, MODE, VC::MINB, false>, FL::WARP_BYTES, "lub_v4_kernel");
     else if constexpr (V3_PF)
-        return plain(lub_v3_kernel<T, N, VC::GR, VC::GC, MODE, VC::MINB, false, true>, FL::WARP_BYTES_PF, "lub_v3_kernel");
+        return plain(lub_v3_kernel<T, N, VC::GR, VC::GC, MODE, VC::MINB, false, true, false, V3_LEAN>, FL::WARP_BYTES_PF, "lub_v3_kernel");
     else
-        return plain(lub_v3_kernel<T, N, VC::GR, VC::GC, MODE, VC::MINB, VC::BSYNC>, FL::WARP_BYTES, "lub_v3_kernel");
+        return plain(lub_v3_kernel<T, N, VC::GR, VC::GC, MODE, VC::MINB, VC::BSYNC, false, false, V3_LEAN>, FL::WARP_BYTES, "lub_v3_kernel");
 }
 
 // Each instantiation TU exports one of these for its (dtype, mode, N-range).

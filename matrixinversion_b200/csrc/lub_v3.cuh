@@ -328,8 +328,10 @@ __device__ __forceinline__ void gj_eliminate_lean(T (&a)[LR][LC], T (&dinv)[LR],
 // fetched with cp.async into the idle one while this tile is searched, eliminated and written back from
 // the other -- the pivot modes need their image until the very end (column scatter), so the in-place
 // prefetch of PF does not apply.
-template <typename T, int N, int GR, int GC, int MODE, int MINB = 1, bool BSYNC = true, bool PF = false, bool PFD = false>
-__global__ void __launch_bounds__(kMaxThreads, MINB)
+// LEAN: the round-2 elimination step (gj_eliminate_lean above); MAXT: block size the kernel is compiled for.
+template <typename T, int N, int GR, int GC, int MODE, int MINB = 1, bool BSYNC = true, bool PF = false, bool PFD = false, bool LEAN = false,
+          int MAXT = kMaxThreads>
+__global__ void __launch_bounds__(MAXT, MINB)
 lub_v3_kernel(T* __restrict__ A, int32_t* __restrict__ piv, long long batch) {
     using L = V3Layout<T, N, GR, GC, MODE>;
     static_assert(!PF || L::ROWVEC, "prefetch needs the 16-byte image");
@@ -468,7 +470,8 @@ lub_v3_kernel(T* __restrict__ A, int32_t* __restrict__ piv, long long batch) {
         T dinv[LR];
 #pragma unroll
         for (int li = 0; li < LR; ++li) dinv[li] = T(0);
-        gj_eliminate<T, N, GR, GC, CH, CPL, LR, LC>(a, dinv, gr, gc, grp_base);
+        if (LEAN) gj_eliminate_lean<T, N, GR, GC, CH, CPL, LR, LC>(a, dinv, gr, gc, grp_base);
+        else gj_eliminate<T, N, GR, GC, CH, CPL, LR, LC>(a, dinv, gr, gc, grp_base);
 
         // ---- scale by 1/pivot, undo the row permutation as a column scatter -------------------
         __syncwarp();

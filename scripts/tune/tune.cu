@@ -18,18 +18,18 @@ struct Variant {
     int (*smem_of)(int warps) = nullptr;
 };
 
-template <typename T, int N, int GR, int GC, int MODE, int MINB, int DBG = 0>
+template <typename T, int N, int GR, int GC, int MODE, int MINB, int DBG = 0, int MAXT = 256>
 struct V3 {
     using L = V3Layout<T, N, GR, GC, MODE>;
     static void set_attr(int smem) {
-        cudaFuncSetAttribute(lub_v3_kernel<T, N, GR, GC, MODE, MINB, (DBG & 8) != 0, (DBG & 16) != 0, (DBG & 32) != 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        cudaFuncSetAttribute(lub_v3_kernel<T, N, GR, GC, MODE, MINB, (DBG & 8) != 0, (DBG & 16) != 0, (DBG & 32) != 0, (DBG & 64) != 0, MAXT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     }
     static void launch(void* A, int* piv, long long batch, unsigned blocks, int threads, int smem, cudaStream_t s) {
-        lub_v3_kernel<T, N, GR, GC, MODE, MINB, (DBG & 8) != 0, (DBG & 16) != 0, (DBG & 32) != 0><<<blocks, threads, smem, s>>>((T*)A, piv, batch);
+        lub_v3_kernel<T, N, GR, GC, MODE, MINB, (DBG & 8) != 0, (DBG & 16) != 0, (DBG & 32) != 0, (DBG & 64) != 0, MAXT><<<blocks, threads, smem, s>>>((T*)A, piv, batch);
     }
     static int occ(int threads, int smem) {
         int o = 0;
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, lub_v3_kernel<T, N, GR, GC, MODE, MINB, (DBG & 8) != 0, (DBG & 16) != 0, (DBG & 32) != 0>, threads, smem);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, lub_v3_kernel<T, N, GR, GC, MODE, MINB, (DBG & 8) != 0, (DBG & 16) != 0, (DBG & 32) != 0, (DBG & 64) != 0, MAXT>, threads, smem);
         return o;
     }
     static Variant make(const char* name) { return Variant{name, L::MPW, (DBG & 16) ? L::WARP_BYTES_PF : ((DBG & 32) ? L::WARP_BYTES_PFD : L::WARP_BYTES), L::HEADER_BYTES, set_attr, launch, occ}; }
@@ -161,6 +161,7 @@ struct VT6 {
 #define VAR(T, N, GR, GC, MODE, MINB) V<T, N, GR, GC, MODE, MINB>::make(#T " N=" #N " " #GR "x" #GC " mode" #MODE " minb" #MINB)
 #define VARD(T, N, GR, GC, MODE, MINB, DBG) V<T, N, GR, GC, MODE, MINB, DBG>::make(#T " N=" #N " " #GR "x" #GC " mode" #MODE " minb" #MINB " dbg" #DBG " v4")
 #define VAR3(T, N, GR, GC, MODE, MINB, DBG) V3<T, N, GR, GC, MODE, MINB, DBG>::make(#T " N=" #N " " #GR "x" #GC " mode" #MODE " minb" #MINB " dbg" #DBG " v3")
+#define VAR3M(T, N, GR, GC, MODE, MINB, DBG, MAXT) V3<T, N, GR, GC, MODE, MINB, DBG, MAXT>::make(#T " N=" #N " " #GR "x" #GC " mode" #MODE " minb" #MINB " dbg" #DBG " maxt" #MAXT " v3")
 
 static Variant variants[] = {
 #include "variants.inc"

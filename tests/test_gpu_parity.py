@@ -541,7 +541,7 @@ def test_generic_kernel_for_unaligned_even_n():
             # the generic kernel and the aligned path are different operation orders (fp64 N = 32: blocked DMMA): compare
             # relative to the matrix' largest entry, entries near zero carry the absolute rounding of their neighbours
             scale = np.abs(X).max(axis=(1, 2), keepdims=True)
-            tol = 1e-4 if dtype == np.float32 else 1e-11
+            tol = 1e-4 if dtype == np.float32 else 1e-8   # uniform(0,1) matrices under the reference's pivot rule: kappa * growth ~ 1e6
             assert np.all(np.abs(view.cpu().numpy() - X) <= tol * scale), (n, dtype, mode)
         assert flat[0].item() == 123.0 and bool((flat[off + A.size:] == 123.0).all())
 
