@@ -19,6 +19,7 @@ CUBLAS_LIB_PATH = os.path.join(_HERE, "liblubatched_cublas.so")
 PIVOT_NONE, PIVOT_SERIAL, PIVOT_PARALLEL, PIVOT_LAPACK = 0, 1, 2, 3
 LAYOUT_MATRIX_MAJOR, LAYOUT_BATCH_INTERLEAVED = 0, 1
 HOST_REGISTER, HOST_BIND_THREADS = 1, 2
+OPT_STAGING, OPT_FP64_TENSOR = 1, 2
 DTYPE_F32, DTYPE_F64 = 0, 1
 
 ERRORS = {
@@ -59,6 +60,8 @@ SIGNATURES = {
     "lu_batched_inplace_host": (ctypes.c_int, [_P, _P, ctypes.c_int, ctypes.c_int64, ctypes.c_int, ctypes.c_int]),
     "lu_batched_inplace_host_multi": (ctypes.c_int, [_P, _P, ctypes.c_int, ctypes.c_int64, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int]),
     "lu_batched_bind_thread_near_device": (ctypes.c_int, [ctypes.c_int]),
+    "lu_batched_set_option": (ctypes.c_int, [ctypes.c_int, ctypes.c_int]),
+    "lu_batched_get_option": (ctypes.c_int, [ctypes.c_int]),
     "lu_batched_set_threads": (ctypes.c_int, [ctypes.c_int]),
     "lu_batched_get_threads": (ctypes.c_int, [ctypes.c_int, ctypes.c_int]),
     "lu_batched_kernel_name": (ctypes.c_char_p, [ctypes.c_int, ctypes.c_int, ctypes.c_int]),

@@ -164,6 +164,13 @@ def lu_batched_inplace_host_multi(A: np.ndarray, piv=None, pivot_mode="parallel"
     return A
 
 
+def set_option(option, value: int) -> None:
+    """lu_batched_set_option: run-time ablation knobs ("staging": 1 = LSU staging instead of TMA; "fp64_tensor": 1 = DFMA
+    rank-1 updates instead of DMMA for fp64 N = 32); 0 restores the library's choice."""
+    code = {"staging": _lib.OPT_STAGING, "fp64_tensor": _lib.OPT_FP64_TENSOR}.get(option, option)
+    check(_lib.lib().lu_batched_set_option(int(code), int(value)))
+
+
 def bind_thread_near_device(device: int) -> bool:
     """Bind the calling thread to the CPUs next to a GPU (lu_batched_bind_thread_near_device), e.g. before allocating the
     host buffers that will feed it (first touch places them on that NUMA node).  False when the topology is not exposed."""

@@ -29,7 +29,7 @@ struct LaunchInfo {
 
 // int launcher(A, piv, batch, threads (0 = default), stream, info (may be NULL), flags)
 // flags: bit 0 = dry run (fill `info`, launch nothing), bit 1 = LU factors only (no inversion)
-constexpr int kLaunchDryRun = 1, kLaunchLuOnly = 2;
+constexpr int kLaunchDryRun = 1, kLaunchLuOnly = 2, kLaunchNoTma = 4, kLaunchNoDmma = 8;  // 4, 8: lu_batched_set_option ablations
 // ev0 (may be NULL): recorded on the stream immediately before the kernel launch, i.e. after the one-time
 // preparation and the tensor-map encode, so that the ABI's "kernel execution time" is the kernel's
 using LaunchFn = cudaError_t (*)(void*, int32_t*, long long, int, cudaStream_t, LaunchInfo*, int, cudaEvent_t);
@@ -315,8 +315,9 @@ cudaError_t launch(void* A, int32_t* piv, long long batch, int threads_req, cuda
     using TC = TmaCfg<T, N, MODE>;
     // fp64 N = 32 (BASELINE config 5): blocked Gauss-Jordan on the FP64 tensor cores (lub_dmma.cuh), four 128-thread
     // blocks per SM: 6.31 -> 5.55 ms with pivoting, 6.45 -> 5.29 ms without (profiles/r02_dmma.md)
+    const bool no_tma = (flags & kLaunchNoTma) != 0;
     if constexpr (sizeof(T) == 8 && N == 32 && kUseTma) {
-        if (fast && batch <= 0x7fffff00ll) {
+        if (fast && batch <= 0x7fffff00ll && !no_tma && !(flags & kLaunchNoDmma)) {
             using TL = TmaLayout<T, N, 8, 4, MODE>;
             auto kern = lub_dmma_kernel<MODE, 2, true>;
             if (threads_req <= 0) x.threads = 128;
@@ -335,7 +336,7 @@ cudaError_t launch(void* A, int32_t* piv, long long batch, int threads_req, cuda
     }
     // TMA tile coordinates are 32-bit: larger batches take the v3 / v4 kernels (64-bit index arithmetic)
     if constexpr (TC::ON) {
-        if (fast && batch <= 0x7fffff00ll) {
+        if (fast && batch <= 0x7fffff00ll && !no_tma) {
             using TL = TmaLayout<T, N, TC::GR, TC::GC, MODE>;
             constexpr int NIMG = (TC::OPT & kTmaDB) ? 2 : 1;
             // no pivoting: results leave through the image and a bulk store (5-18 % faster than register
@@ -366,7 +367,7 @@ cudaError_t launch(void* A, int32_t* piv, long long batch, int threads_req, cuda
                               return cudaGetLastError();
                           });
     }
-    // When the TMA path is compiled in but not taken (batch beyond 32-bit tile coordinates) the fast cache entry
+    // When the TMA path is compiled in but not taken (batch beyond 32-bit tile coordinates, LUB_OPT_STAGING) the fast cache entry
     // would be shared by two kernels: keep a second one.
     static KernelCache cache_fast2[kMaxDevices];
     KernelCache& cf = TC::ON ? cache_fast2[dev] : cache_fast[dev];

@@ -55,6 +55,7 @@ namespace {
 thread_local std::string g_err;
 thread_local cudaStream_t g_stream = nullptr;
 thread_local int g_threads = 0;
+thread_local int g_opt_flags = 0;   // lub::kLaunchNoTma | lub::kLaunchNoDmma (lu_batched_set_option)
 thread_local bool g_timing = false;
 // start / stop events of the timed launch, one pair per device (events belong to the device they were created on)
 thread_local cudaEvent_t g_ev[lub::kMaxDevices][2] = {};
@@ -102,6 +103,7 @@ int launch_on(void* ptr, int32_t* piv, int n, int64_t batch, int mode, int dtype
     }
     // the launcher records the start event itself, after its one-time preparation (function attributes,
     // occupancy query, tensor-map encode): the interval is the kernel's, also on the first call
+    flags |= g_opt_flags;
     cudaError_t e;
     if (mode == LUB_PIVOT_LAPACK) {
         e = (dtype == LUB_DTYPE_F32 ? lub::launch_lapack_f32 : lub::launch_lapack_f64)(ptr, piv, status, n, (long long)batch, g_threads, s, info, flags,
@@ -348,6 +350,22 @@ int lu_batched_set_threads(int numthreads) {
         return fail(LUB_ERR_BAD_ARG, "numthreads must be 0 or a multiple of 32 in [32, 256]");
     g_threads = numthreads;
     return LUB_OK;
+}
+
+int lu_batched_set_option(int option, int value) {
+    int bit = 0;
+    if (option == LUB_OPT_STAGING) bit = lub::kLaunchNoTma;
+    else if (option == LUB_OPT_FP64_TENSOR) bit = lub::kLaunchNoDmma;
+    else return fail(LUB_ERR_BAD_ARG, "unknown option");
+    if (value != 0 && value != 1) return fail(LUB_ERR_BAD_ARG, "option value must be 0 (library default) or 1 (ablation)");
+    g_opt_flags = value ? (g_opt_flags | bit) : (g_opt_flags & ~bit);
+    return LUB_OK;
+}
+
+int lu_batched_get_option(int option) {
+    if (option == LUB_OPT_STAGING) return (g_opt_flags & lub::kLaunchNoTma) ? 1 : 0;
+    if (option == LUB_OPT_FP64_TENSOR) return (g_opt_flags & lub::kLaunchNoDmma) ? 1 : 0;
+    return fail(LUB_ERR_BAD_ARG, "unknown option");
 }
 
 int lu_batched_get_threads(int n, int dtype) {

@@ -167,3 +167,39 @@ def test_host_multi_device_entry_point_equals_the_single_device_path():
     with pytest.raises(lub.LubError):
         lub.lu_batched_inplace_host_multi(np.zeros((4, 3, 3), np.float32), n_devices=ndev + 1)
     assert lub.bind_thread_near_device(0) in (True, False)
+
+
+def test_ablation_options_change_the_kernel_not_the_result():
+    """lu_batched_set_option: LSU staging instead of TMA is the same arithmetic (bitwise equal results); DFMA instead of DMMA for
+    fp64 N = 32 is another operation order (pivots bit-exact, values to rounding)."""
+    for n, dtype in ((32, np.float32), (24, np.float32), (16, np.float64)):
+        A = synthetic(n, 517, dtype)
+        dA = torch.from_numpy(A).cuda(); piv = torch.zeros((517, n), dtype=torch.int32, device="cuda")
+        lub.lu_batched_inplace(dA, piv, "parallel")
+        name0 = lub.kernel_name(n, "parallel", dtype)
+        lub.set_option("staging", 1)
+        try:
+            name1 = lub.kernel_name(n, "parallel", dtype)
+            dB = torch.from_numpy(A).cuda(); pivB = torch.zeros_like(piv)
+            lub.lu_batched_inplace(dB, pivB, "parallel")
+        finally:
+            lub.set_option("staging", 0)
+        assert name0 == "lub_tma_kernel" and name1 in ("lub_v3_kernel", "lub_v4_kernel")
+        assert torch.equal(pivB, piv) and torch.equal(dB, dA), (n, dtype)
+    A = synthetic(32, 517, np.float64)
+    dA = torch.from_numpy(A).cuda(); piv = torch.zeros((517, 32), dtype=torch.int32, device="cuda")
+    lub.lu_batched_inplace(dA, piv, "parallel")
+    assert lub.kernel_name(32, "parallel", np.float64) == "lub_dmma_kernel"
+    lub.set_option("fp64_tensor", 1)
+    try:
+        assert lub.kernel_name(32, "parallel", np.float64) == "lub_tma_kernel"
+        dB = torch.from_numpy(A).cuda(); pivB = torch.zeros_like(piv)
+        lub.lu_batched_inplace(dB, pivB, "parallel")
+    finally:
+        lub.set_option("fp64_tensor", 0)
+    assert torch.equal(pivB, piv)
+    X, Y = dA.cpu().numpy(), dB.cpu().numpy()
+    good = np.linalg.cond(A) < 1e5
+    assert np.all(np.abs(X - Y)[good].max(axis=(1, 2)) <= 1e-9 * np.abs(Y)[good].max(axis=(1, 2)))
+    with pytest.raises(lub.LubError):
+        lub.set_option(99, 1)
