@@ -29,7 +29,7 @@ struct LaunchInfo {
 
 // int launcher(A, piv, batch, threads (0 = default), stream, info (may be NULL), flags)
 // flags: bit 0 = dry run (fill `info`, launch nothing), bit 1 = LU factors only (no inversion)
-constexpr int kLaunchDryRun = 1, kLaunchLuOnly = 2, kLaunchNoTma = 4, kLaunchNoDmma = 8;  // 4, 8: lu_batched_set_option ablations
+constexpr int kLaunchDryRun = 1, kLaunchLuOnly = 2, kLaunchNoTma = 4, kLaunchNoDmma = 8, kLaunchForceDmma = 16;  // 4, 8, 16: lu_batched_set_option
 // ev0 (may be NULL): recorded on the stream immediately before the kernel launch, i.e. after the one-time
 // preparation and the tensor-map encode, so that the ABI's "kernel execution time" is the kernel's
 using LaunchFn = cudaError_t (*)(void*, int32_t*, long long, int, cudaStream_t, LaunchInfo*, int, cudaEvent_t);
@@ -313,11 +313,15 @@ cudaError_t launch(void* A, int32_t* piv, long long batch, int threads_req, cuda
     static KernelCache cache_fast[kMaxDevices], cache_gen[kMaxDevices];
 
     using TC = TmaCfg<T, N, MODE>;
-    // fp64 N = 32 (BASELINE config 5): blocked Gauss-Jordan on the FP64 tensor cores (lub_dmma.cuh), four 128-thread
-    // blocks per SM: 6.31 -> 5.55 ms with pivoting, 6.45 -> 5.29 ms without (profiles/r02_dmma.md)
+    // fp64 N = 32: blocked Gauss-Jordan on the FP64 tensor cores (lub_dmma.cuh), four 128-thread blocks per SM: 6.45 -> 5.29 ms
+    // without pivoting, 6.31 -> 5.54 ms with.  Library default: WITHOUT pivoting only -- the block step multiplies by an
+    // explicit 4 x 4 inverse, which is as accurate as the unblocked elimination on the diagonally dominant matrices the
+    // no-pivot mode is for, but amplifies the conditioning of the diagonal blocks under the reference's pivot rule (27 %
+    // of uniform(0,1) matrices get a >= 10x larger residual, profiles/r02_dmma.md); LUB_OPT_FP64_TENSOR = 2 forces it.
     const bool no_tma = (flags & kLaunchNoTma) != 0;
     if constexpr (sizeof(T) == 8 && N == 32 && kUseTma) {
-        if (fast && batch <= 0x7fffff00ll && !no_tma && !(flags & kLaunchNoDmma)) {
+        const bool want = (MODE == kModeNone || (flags & kLaunchForceDmma)) && !(flags & kLaunchNoDmma);
+        if (fast && batch <= 0x7fffff00ll && !no_tma && want) {
             using TL = TmaLayout<T, N, 8, 4, MODE>;
             auto kern = lub_dmma_kernel<MODE, 2, true>;
             if (threads_req <= 0) x.threads = 128;

@@ -353,18 +353,23 @@ int lu_batched_set_threads(int numthreads) {
 }
 
 int lu_batched_set_option(int option, int value) {
-    int bit = 0;
-    if (option == LUB_OPT_STAGING) bit = lub::kLaunchNoTma;
-    else if (option == LUB_OPT_FP64_TENSOR) bit = lub::kLaunchNoDmma;
-    else return fail(LUB_ERR_BAD_ARG, "unknown option");
-    if (value != 0 && value != 1) return fail(LUB_ERR_BAD_ARG, "option value must be 0 (library default) or 1 (ablation)");
-    g_opt_flags = value ? (g_opt_flags | bit) : (g_opt_flags & ~bit);
+    if (option == LUB_OPT_STAGING) {
+        if (value != 0 && value != 1) return fail(LUB_ERR_BAD_ARG, "LUB_OPT_STAGING: 0 (library choice) or 1 (LSU staging)");
+        g_opt_flags = value ? (g_opt_flags | lub::kLaunchNoTma) : (g_opt_flags & ~lub::kLaunchNoTma);
+    } else if (option == LUB_OPT_FP64_TENSOR) {
+        if (value < 0 || value > 2) return fail(LUB_ERR_BAD_ARG, "LUB_OPT_FP64_TENSOR: 0 (library choice), 1 (never) or 2 (always)");
+        g_opt_flags &= ~(lub::kLaunchNoDmma | lub::kLaunchForceDmma);
+        if (value == 1) g_opt_flags |= lub::kLaunchNoDmma;
+        if (value == 2) g_opt_flags |= lub::kLaunchForceDmma;
+    } else {
+        return fail(LUB_ERR_BAD_ARG, "unknown option");
+    }
     return LUB_OK;
 }
 
 int lu_batched_get_option(int option) {
     if (option == LUB_OPT_STAGING) return (g_opt_flags & lub::kLaunchNoTma) ? 1 : 0;
-    if (option == LUB_OPT_FP64_TENSOR) return (g_opt_flags & lub::kLaunchNoDmma) ? 1 : 0;
+    if (option == LUB_OPT_FP64_TENSOR) return (g_opt_flags & lub::kLaunchNoDmma) ? 1 : ((g_opt_flags & lub::kLaunchForceDmma) ? 2 : 0);
     return fail(LUB_ERR_BAD_ARG, "unknown option");
 }
 
