@@ -1,0 +1,370 @@
+// lub_bulk.cuh -- the in-register Gauss-Jordan kernel (lub_v3.cuh) staged by 1-D bulk copies, for the sizes
+// whose rows are NOT whole 16-byte multiples (every N that is not a multiple of 4 in fp32, odd N in fp64):
+// a tensor map cannot describe them (global strides must be 16-byte multiples), so lub_v3_kernel moved
+// their tiles through the LSU (LDG/LDGSTS + STS, LDS + STG: ~170 issued instructions per fp32 N = 31 matrix
+// and an un-prefetched wait, profiles/r02_prof_n31_f32_parallel.md).  But a warp tile -- MPW whole
+// matrices, contiguous in `T A[batch][n][n]` (templated/luBatchedInplace.cuh:89-97) -- is a contiguous
+// byte span, and cp.async.bulk (UBLKCP) moves such a span with ONE instruction each way:
+//
+//   * load: the 16-byte aligned part of the span, [s & ~15, e & ~15), by one cp.async.bulk that completes on
+//     the image's mbarrier; the image starts at buf + (s & 15) so that global and shared 16-byte chunks line
+//     up.  Up to three words of a ragged end travel by 4-byte cp.async.  Bytes of the neighbouring tile that
+//     the round-down drags along are never used.
+//   * two images per warp: the next tile is requested right after the register load, so no warp waits
+//     on HBM for its input (as the TMA kernel's DB option, lub_tma.cuh);
+//   * store: results go into the image (pivot modes: the column scatter that undoes the row permutation),
+//     the aligned interior leaves by one cp.async.bulk, up to three words at either end by plain stores --
+//     neighbouring tiles never write each other's bytes.
+//
+// The image is dense (row stride N): odd N makes every column walk conflict-free, N = 2 mod 4 two-way.
+//
+// Pivot search for parallel pivoting with N not a power of two (prepass_rowpos below): the reference tree
+// (parallel_pivot/luBatchedInplace.cuh:12-44) only merges some of its slots into slot 0, so whether a row is
+// a candidate at step k depends on WHERE it sits.  lub_fast.cuh searches with lane = position and fetches
+// the value through a run-time row address (16 issued instructions per step).  Here lane = ORIGINAL row,
+// as in the row-wise search: its column entries come from static addresses, and the lane carries its
+// row's current position as a one-hot word.
+#pragma once
+#include "lub_tma.cuh"
+
+namespace lub {
+
+__device__ __forceinline__ void bulk_load(void* dst, const void* src, unsigned bytes, void* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void bulk_store(void* dst, const void* src, unsigned bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(smem_u32(src)), "r"(bytes) : "memory");
+}
+
+template <typename T, int N, int GR, int GC, int MODE>
+struct BulkLayout {
+    static constexpr int ES = sizeof(T);
+    static constexpr int EPV = 16 / ES;
+    // widest vector the dense rows allow: the image inherits the alignment of global memory
+    static constexpr int CH = (N % EPV == 0) ? EPV : ((EPV == 4 && N % 2 == 0) ? 2 : 1);
+    static constexpr int G = GR * GC;
+    static_assert(G >= 1 && G <= 32 && (32 % G) == 0, "G must divide 32");
+    static constexpr int MPW = 32 / G;
+    static constexpr int CPR = N / CH;
+    static constexpr int CPL = cdiv_(CPR, GC);
+    static constexpr int LC = CPL * CH;
+    static constexpr int LR = cdiv_(N, GR);
+    static constexpr int P = N, MS = N * N;
+    static constexpr int SPAN_BYTES = MPW * MS * ES;
+    static constexpr bool ALIGNED = (SPAN_BYTES % 16) == 0;  // every full tile starts on 16 bytes
+    static constexpr int IMG_BYTES = roundup_(SPAN_BYTES, 16) + 16;
+    static constexpr int PERM_BYTES = (MODE != kModeNone) ? roundup_(MPW * N * 4, 16) : 0;
+    static constexpr int HEADER_BYTES = 64;
+    static constexpr int warp_bytes(int nimg) { return nimg * IMG_BYTES + PERM_BYTES + 16; }
+    static constexpr int smem_bytes(int warps, int nimg) { return HEADER_BYTES + warps * warp_bytes(nimg); }
+};
+
+// Row-wise pivot search in floating point (see prepass_rowwise_swz, lub_tma.cuh) on a plain image with row
+// stride P: serial pivoting, and parallel pivoting when the reference tree reaches all of its slots.
+template <int N, int MODE, int P, int MS, int MI>
+__device__ __forceinline__ void prepass_rowwise_f32(const float* __restrict__ img0, int* __restrict__ perm0,
+                                                    const int8_t* __restrict__ slot_rank, int lane) {
+    const int roff = ((lane < N) ? lane : 0) * P;
+    float alive[MI], when[MI];
+#pragma unroll
+    for (int m = 0; m < MI; ++m) { alive[m] = (lane < N) ? 1.0f : 0.0f; when[m] = 0.0f; }
+#pragma unroll
+    for (int k = 0; k < N - 1; ++k) {
+        float v[MI], mx[MI];
+#pragma unroll
+        for (int m = 0; m < MI; ++m) v[m] = img0[m * MS + roff + k] * alive[m];
+#pragma unroll
+        for (int m = 0; m < MI; ++m) mx[m] = warp_max_abs(v[m]);
+#pragma unroll
+        for (int m = 0; m < MI; ++m) {
+            const float hit = (fabsf(v[m]) == mx[m]) ? 1.0f : 0.0f;
+            when[m] = fmaf(hit, (float)k, when[m]);
+            alive[m] = fmaf(-hit, alive[m], alive[m]);
+        }
+    }
+#pragma unroll
+    for (int m = 0; m < MI; ++m) {
+        // every row must have ended on a position of its own (a shared maximum retires two rows at once; NaNs
+        // never hit): one REDUX.OR over the one-hot positions, warp-uniform
+        const float wf = (alive[m] != 0.0f) ? (float)(N - 1) : when[m];
+        const int pos = (int)fminf(wf, 31.0f);
+        constexpr unsigned ALL = (N >= 32) ? 0xffffffffu : ((1u << N) - 1u);
+        const bool ok = __reduce_or_sync(0xffffffffu, (lane < N) ? (1u << pos) : 0u) == ALL;
+        if (ok) {
+            if (lane < N) perm0[m * N + pos] = lane;
+        } else {
+            prepass_exact<float, N, MODE, P>(img0 + m * MS, perm0 + m * N, slot_rank, lane);
+        }
+    }
+}
+
+// Position-aware row-wise search (parallel pivoting, N not a power of two).  Lane r owns original row r and
+// carries pb = 1 << (the position row r sits at).  Step k:
+//   candidates  = rows whose position is k (the seed every tree slot starts from) or k + 1 + t for a slot t
+//                 the tree merges into slot 0: (pb & VM_k) != 0, VM_k a compile-time mask;
+//   pick        = the candidate with the largest |A[r][k]| (un-eliminated entries): one CREDUX;
+//   swap        = the picked row takes position k for good, the row that sat at k takes the picked row's
+//                 position (one REDUX.OR broadcasts it; both lanes XOR their word with hp ^ (1 << k)).
+// (A variant that hands the displaced row its next validity bit with a VOTE.ANY, so that the REDUX.OR leaves the
+// critical path, issued 4 more instructions per step and was 10 % slower on N = 31: the kernel is bound by issue
+// slots, not by this chain's latency -- profiles/r02_tune_bulk.md.)
+// A step with several equal maxima (or an all-zero column, where every lane "hits") leaves two lanes on one
+// position: then the N one-hot words no longer cover N positions once each, and the matrix is redone by the
+// exact search, which also knows the tree's tie order (same rule as the other fast searches).
+template <typename T, int N, int MODE, int P, int MS, int MI>
+__device__ __forceinline__ void prepass_rowpos(const T* __restrict__ img0, int* __restrict__ perm0,
+                                               const int8_t* __restrict__ slot_rank, int lane) {
+    using U = typename FpBits<T>::U;
+    constexpr unsigned ALL = (N >= 32) ? 0xffffffffu : ((1u << N) - 1u);
+    constexpr unsigned REACH = ReachMask<N>::value;
+    const int roff = ((lane < N) ? lane : 0) * P;
+    unsigned pb[MI];
+#pragma unroll
+    for (int m = 0; m < MI; ++m) pb[m] = (lane < N) ? (1u << lane) : 0u;
+#pragma unroll
+    for (int k = 0; k < N - 1; ++k) {
+        const unsigned vmask = ((MODE == kModeParallel) ? ((REACH << (k + 1)) | (1u << k)) : (ALL << k)) & ALL;
+        if constexpr (sizeof(T) == 4) {
+            float v[MI], mx[MI];
+#pragma unroll
+            for (int m = 0; m < MI; ++m) v[m] = sel_t((pb[m] & vmask) != 0u, img0[m * MS + roff + k], 0.0f);
+#pragma unroll
+            for (int m = 0; m < MI; ++m) mx[m] = warp_max_abs(v[m]);
+#pragma unroll
+            for (int m = 0; m < MI; ++m) {
+                const bool hit = fabsf(v[m]) == mx[m];
+                const unsigned hp = __reduce_or_sync(0xffffffffu, hit ? pb[m] : 0u);
+                // the picked row and the row at position k swap places: both XOR with (hp ^ bit k)
+                if (hit || pb[m] == (1u << k)) pb[m] ^= hp ^ (1u << k);
+            }
+        } else {
+            U v[MI], mx[MI];
+#pragma unroll
+            for (int m = 0; m < MI; ++m) v[m] = ((pb[m] & vmask) != 0u) ? FpBits<T>::absbits(img0[m * MS + roff + k]) : U(0);
+#pragma unroll
+            for (int m = 0; m < MI; ++m) mx[m] = warp_max_bits(v[m]);
+#pragma unroll
+            for (int m = 0; m < MI; ++m) {
+                const bool hit = v[m] == mx[m];
+                const unsigned hp = __reduce_or_sync(0xffffffffu, hit ? pb[m] : 0u);
+                // the picked row and the row at position k swap places: both XOR with (hp ^ bit k)
+                if (hit || pb[m] == (1u << k)) pb[m] ^= hp ^ (1u << k);
+            }
+        }
+    }
+#pragma unroll
+    for (int m = 0; m < MI; ++m) {
+        const unsigned cover = __reduce_or_sync(0xffffffffu, pb[m]);
+        const unsigned odd = __ballot_sync(0xffffffffu, __popc(pb[m]) != ((lane < N) ? 1 : 0));
+        if (cover == ALL && odd == 0u) {  // warp-uniform: every row on one position, every position taken
+            if (lane < N) perm0[m * N + (__ffs((int)pb[m]) - 1)] = lane;
+        } else {
+            prepass_exact<T, N, MODE, P>(img0 + m * MS, perm0 + m * N, slot_rank, lane);
+        }
+    }
+}
+
+// OPT bits
+constexpr int kBulkLean = 1;      // gj_eliminate_lean
+constexpr int kBulkOldSearch = 2; // the position-wise search of lub_fast.cuh (for comparison)
+constexpr int kBulkSingle = 4;    // one image per warp (no prefetch)
+constexpr int kBulkGroupSearch = 16; // N <= 16: every lane group searches its own matrix (prepass_group) instead of warp-wide searches
+
+template <typename T, int N, int GR, int GC, int MODE, int MINB = 1, bool BSYNC = false, int OPT = kBulkLean, int MAXT = kMaxThreads>
+__global__ void __launch_bounds__(MAXT, MINB)
+lub_bulk_kernel(T* __restrict__ A, int32_t* __restrict__ piv, long long batch) {
+    using L = BulkLayout<T, N, GR, GC, MODE>;
+    constexpr bool LEAN = (OPT & kBulkLean) != 0, OLDS = (OPT & kBulkOldSearch) != 0;
+    constexpr int NIMG = (OPT & kBulkSingle) ? 1 : 2;
+    constexpr int G = L::G, MPW = L::MPW, LR = L::LR, LC = L::LC, CH = L::CH, CPL = L::CPL, CPR = L::CPR;
+    constexpr int P = L::P, MS = L::MS, ES = L::ES;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    const int nwarps = blockDim.x >> 5;
+    int8_t* slot_rank = reinterpret_cast<int8_t*>(smem_raw);
+    constexpr int WARP_BYTES = NIMG * L::IMG_BYTES + L::PERM_BYTES + 16;
+    unsigned char* wbase = smem_raw + L::HEADER_BYTES + (size_t)warp * WARP_BYTES;
+    int* perm_all = reinterpret_cast<int*>(wbase + NIMG * L::IMG_BYTES);
+    unsigned long long* bar0 = reinterpret_cast<unsigned long long*>(wbase + NIMG * L::IMG_BYTES + L::PERM_BYTES);
+
+    if (MODE == kModeParallel && threadIdx.x < N) slot_rank[threadIdx.x] = (int8_t)tree_slot_rank(threadIdx.x, N);
+    if (lane == 0) { mbar_init(bar0, 1); mbar_init(bar0 + 1, 1); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    __syncthreads();
+
+    const int g = lane % G;
+    const int ml = lane / G;
+    const int gr = g / GC;
+    const int gc = g % GC;
+    const int grp_base = ml * G;
+
+    const long long ntiles = (batch + MPW - 1) / MPW;
+    const long long tstride = (long long)gridDim.x * nwarps;
+    const unsigned char* Ab = reinterpret_cast<const unsigned char*>(A);
+    const long long batch_bytes = batch * (long long)(MS * ES);
+
+    // lane 0: request the span of `tile` into image buffer `buf`, completion on `bar` (+ its own cp.async group)
+    auto request = [&](long long tile, unsigned char* buf, unsigned long long* bar) {
+        const long long s = tile * (long long)L::SPAN_BYTES;
+        long long e = s + L::SPAN_BYTES;
+        if (e > batch_bytes) e = batch_bytes;
+        const long long s16 = s & ~15ll, e16 = e & ~15ll;
+        const unsigned bytes = (unsigned)(e16 - s16);
+        mbar_expect_tx(bar, bytes);
+        if (bytes) bulk_load(buf, Ab + s16, bytes, bar);
+        for (long long b = e16; b < e; b += 4) cp_async4(buf + (b - s16), Ab + b);  // ragged end: at most three words
+        cp_async_commit();
+    };
+
+    unsigned iter = 0;
+    if (NIMG == 2 && lane == 0) {
+        const long long t0 = (long long)blockIdx.x * nwarps + warp;
+        if (t0 < ntiles) request(t0, wbase, bar0);
+    }
+#pragma unroll 1
+    for (long long tbase = (long long)blockIdx.x * nwarps; tbase < ntiles; tbase += tstride) {
+        if (BSYNC) __syncthreads();
+        const long long tile = tbase + warp;
+        if (tile >= ntiles) continue;
+        const long long first = tile * MPW;
+        const int nm = (batch - first < MPW) ? (int)(batch - first) : MPW;
+        const long long s = tile * (long long)L::SPAN_BYTES;
+        const long long e = s + (long long)nm * (MS * ES);
+        const unsigned mis = L::ALIGNED ? 0u : (unsigned)(s & 15);
+
+        const unsigned cur = (NIMG == 2) ? (iter & 1u) : 0u;
+        unsigned char* buf = wbase + cur * L::IMG_BYTES;
+        unsigned long long* bar = bar0 + cur;
+        const unsigned parity = (NIMG == 2) ? ((iter >> 1) & 1u) : (iter & 1u);
+        ++iter;
+        if (NIMG == 1 && lane == 0) {
+            tma_store_wait_read();  // last round's tile has left the image
+            request(tile, buf, bar);
+        }
+        if (lane == 0) cp_async_wait<0>();
+        mbar_wait(bar, parity);
+        __syncwarp();
+
+        T* img = reinterpret_cast<T*>(buf + mis);
+        T* mimg = img + ml * MS;
+        int* perm = perm_all + ml * N;
+        if (MODE != kModeNone && N <= 16 && (OPT & kBulkGroupSearch) != 0) {
+            prepass_group<T, N, G, MODE, P>(mimg, perm, slot_rank, g);
+            __syncwarp();
+        } else if (MODE != kModeNone) {
+            constexpr int MI = (MPW < 4) ? MPW : 4;
+#pragma unroll 1
+            for (int m = 0; m < MPW; m += MI) {
+                if constexpr (OLDS || (sizeof(T) == 8 && RowwiseOk<N, MODE>::value))
+                    prepass_warp<T, N, MODE, P, MS, MI, false, false>(img + m * MS, perm_all + m * N, slot_rank, lane);
+                else if constexpr (RowwiseOk<N, MODE>::value)
+                    prepass_rowwise_f32<N, MODE, P, MS, MI>(img + m * MS, perm_all + m * N, slot_rank, lane);
+                else
+                    prepass_rowpos<T, N, MODE, P, MS, MI>(img + m * MS, perm_all + m * N, slot_rank, lane);
+            }
+            __syncwarp();
+        }
+
+        // ---- registers <- image: rows permuted, LR x LC block per lane ---------------------
+        T a[LR][LC];
+#pragma unroll
+        for (int li = 0; li < LR; ++li) {
+            const int i = li * GR + gr;
+            const bool rok = (li * GR + GR - 1 < N) || (i < N);
+            int prow = rok ? i : 0;
+            if (MODE != kModeNone) prow = rok ? min((unsigned)perm[i], (unsigned)(N - 1)) : 0;  // clamped: NaN inputs stay memory-safe
+            const T* rowp = mimg + prow * P;
+#pragma unroll
+            for (int q = 0; q < CPL; ++q) {
+                const int cq = gc * CPL + q;
+                const bool ok = rok && ((GC * CPL <= CPR) || (cq < CPR));
+                if (ok) {
+                    ld_vec<T, CH>(rowp + cq * CH, &a[li][q * CH]);
+                } else {
+#pragma unroll
+                    for (int w = 0; w < CH; ++w) a[li][q * CH + w] = T(0);
+                }
+            }
+        }
+
+        if (NIMG == 2) {  // the other image: last round's tile left it through a bulk store issued a whole search ago
+            const long long nxt = tile + tstride;
+            if (lane == 0 && nxt < ntiles) {
+                tma_store_wait_read();
+                request(nxt, wbase + (cur ^ 1u) * L::IMG_BYTES, bar0 + (cur ^ 1u));
+            }
+        }
+
+        T dinv[LR];
+#pragma unroll
+        for (int li = 0; li < LR; ++li) dinv[li] = T(0);
+        if (LEAN) gj_eliminate_lean<T, N, GR, GC, CH, CPL, LR, LC>(a, dinv, gr, gc, grp_base);
+        else gj_eliminate<T, N, GR, GC, CH, CPL, LR, LC>(a, dinv, gr, gc, grp_base);
+
+        // ---- scale by 1/pivot; results into the image (pivot modes: column scatter = un-permute) ----
+#pragma unroll
+        for (int li = 0; li < LR; ++li) {
+#pragma unroll
+            for (int lj = 0; lj < LC; ++lj) a[li][lj] *= dinv[li];
+        }
+        if (MODE == kModeNone) {
+            __syncwarp();  // every lane has its block: the image may be overwritten
+#pragma unroll
+            for (int li = 0; li < LR; ++li) {
+                const int i = li * GR + gr;
+                const bool rok = (li * GR + GR - 1 < N) || (i < N);
+#pragma unroll
+                for (int q = 0; q < CPL; ++q) {
+                    const int cq = gc * CPL + q;
+                    if (rok && ((GC * CPL <= CPR) || (cq < CPR))) st_vec<T, CH>(mimg + i * P + cq * CH, &a[li][q * CH]);
+                }
+            }
+        } else {
+            int pcol[LC];
+#pragma unroll
+            for (int lj = 0; lj < LC; ++lj) {
+                const int j = gc * LC + lj;
+                pcol[lj] = ((GC * LC <= N) || (j < N)) ? (int)min((unsigned)perm[j], (unsigned)(N - 1)) : -1;
+            }
+            __syncwarp();  // all lanes hold their blocks and columns: the image may be overwritten
+#pragma unroll
+            for (int li = 0; li < LR; ++li) {
+                const int i = li * GR + gr;
+                const bool rok = (li * GR + GR - 1 < N) || (i < N);
+#pragma unroll
+                for (int lj = 0; lj < LC; ++lj)
+                    if (rok && ((GC * LC <= N) || (pcol[lj] >= 0))) mimg[i * P + pcol[lj]] = a[li][lj];
+            }
+        }
+        fence_proxy_async();  // generic-proxy writes -> visible to the bulk-copy unit
+        __syncwarp();
+        {
+            // aligned interior by one bulk store; up to three words at either end by plain stores
+            const long long s16u = (s + 15) & ~15ll, e16 = e & ~15ll;
+            unsigned char* gdst = reinterpret_cast<unsigned char*>(A);
+            if (lane == 0) {
+                if (e16 > s16u) bulk_store(gdst + s16u, buf + mis + (s16u - s), (unsigned)(e16 - s16u));
+                tma_store_commit();
+            }
+            const int hw = (int)(s16u - s) >> 2, tw = (int)(e - e16) >> 2;  // head / tail words (0..3)
+            if (!L::ALIGNED && lane < hw)
+                *reinterpret_cast<unsigned*>(gdst + s + 4 * lane) = *reinterpret_cast<const unsigned*>(buf + mis + 4 * lane);
+            if (lane >= 4 && lane < 4 + tw)
+                *reinterpret_cast<unsigned*>(gdst + e16 + 4 * (lane - 4)) = *reinterpret_cast<const unsigned*>(buf + mis + (e16 - s) + 4 * (lane - 4));
+        }
+        int32_t* pivp = piv;
+        asm volatile("" : "+l"(pivp));  // opaque: no second copy of the tile loop for piv == NULL
+        if (pivp != nullptr) {
+            int32_t* pdst = pivp + first * N;
+            for (int x = lane; x < nm * N; x += 32)
+                pdst[x] = (MODE != kModeNone) ? perm_all[x] : (x % N);
+        }
+        __syncwarp();
+    }
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // stores complete
+}
+
+}  // namespace lub

@@ -13,6 +13,7 @@
 #include "lub_v4.cuh"
 #include "lub_tma.cuh"
 #include "lub_dmma.cuh"
+#include "lub_bulk.cuh"
 
 namespace lub {
 
@@ -185,6 +186,54 @@ struct TmaCfg {
     static constexpr int GR = c.gr, GC = c.gc;
     static constexpr bool BSYNC = c.bsync;
     static constexpr int OPT = c.opt, MAXT = c.maxt, THREADS = c.threads;
+};
+
+// Which configurations run the bulk-copy staged kernel (lub_bulk.cuh): the sizes whose rows are not 16-byte
+// multiples, i.e. the ones a tensor map cannot describe.  Lane grid as pick_v3_cfg, with the vector width the
+// dense image allows; two images per warp, so the block shape follows from shared memory: two (three, four for
+// small N) 256-thread blocks per SM where they fit, else one 384-thread block.
+constexpr Cfg pick_bulk_cfg(int n, int es) {
+    const int epv = 16 / es;
+    const int ch = (n % epv == 0) ? epv : ((epv == 4 && n % 2 == 0) ? 2 : 1);
+    const int cpr = n / ch;
+    const int budget = (es == 4) ? 64 : 36;
+    for (int g = 1; g <= 32; g *= 2) {
+        if (g == 2) continue;
+        int best_cost = 1 << 30;
+        Cfg best{0, 0};
+        for (int gr = 1; gr <= g; gr *= 2) {
+            const int gc = g / gr;
+            const int lr = cdiv(n, gr), lc = cdiv(cpr, gc) * ch;
+            if (lr * lc > budget) continue;
+            const int cost = 64 * ((gc > 1 ? lr : 0) + (gr > 1 ? lc : 0)) + lr;
+            if (cost < best_cost) { best_cost = cost; best = Cfg{gr, gc}; }
+        }
+        if (best.gr) return best;
+    }
+    return Cfg{4, 8};
+}
+struct BulkChoice { bool on; int gr, gc, minb, maxt, threads, opt; };
+#ifndef LUB_BULK_MIN_N
+#define LUB_BULK_MIN_N 5
+#endif
+constexpr BulkChoice pick_bulk(int n, int es, int mode) {
+    const Cfg c = pick_bulk_cfg(n, es);
+    if (es != 4 || n % 4 == 0 || n < LUB_BULK_MIN_N) return BulkChoice{false, c.gr, c.gc, 1, kMaxThreads, 256, 0};
+    const int mpw = 32 / (c.gr * c.gc);
+    const int img = (mpw * n * n * es + 15) / 16 * 16 + 16;
+    const int perm = (mode != kModeNone) ? (mpw * n * 4 + 15) / 16 * 16 : 0;
+    const int wb = 2 * img + perm + 16;
+    int minb = pick_minb(n, es, mode != kModeNone);
+    while (minb > 1 && minb * (64 + 8 * wb + 1024) > 233472) --minb;
+    const int opt = (n >= 25 ? kBulkLean : 0) | (n <= 16 ? kBulkGroupSearch : 0);
+    if (minb == 1) return BulkChoice{true, c.gr, c.gc, 1, 384, 384, opt};
+    return BulkChoice{true, c.gr, c.gc, minb, kMaxThreads, 256, opt};
+}
+template <typename T, int N, int MODE>
+struct BulkCfg {
+    static constexpr BulkChoice c = pick_bulk(N, (int)sizeof(T), MODE);
+    static constexpr bool ON = kUseTma && c.on;
+    static constexpr int GR = c.gr, GC = c.gc, MINB = c.minb, MAXT = c.maxt, THREADS = c.threads, OPT = c.opt;
 };
 
 constexpr int kMaxDevices = 64;
@@ -360,6 +409,22 @@ cudaError_t launch(void* A, int32_t* piv, long long batch, int threads_req, cuda
                               });
         }
     }
+    // rows that are not 16-byte multiples: 1-D bulk copies instead of a tensor map (lub_bulk.cuh); any batch size
+    using BC = BulkCfg<T, N, MODE>;
+    if constexpr (BC::ON) {
+        if (fast && !no_tma) {
+            using BL = BulkLayout<T, N, BC::GR, BC::GC, MODE>;
+            auto kern = lub_bulk_kernel<T, N, BC::GR, BC::GC, MODE, BC::MINB, false, BC::OPT, BC::MAXT>;
+            if (threads_req <= 0) x.threads = BC::THREADS;
+            return run_kernel(kern, cache_fast[dev], x, BC::MAXT, [](int w) { return BL::smem_bytes(w, 2); }, BL::MPW, BL::G, "lub_bulk_kernel",
+                              [&](unsigned blocks, int smem) {
+                                  cudaError_t e = start();
+                                  if (e != cudaSuccess) return e;
+                                  kern<<<blocks, x.threads, smem, stream>>>(At, piv, batch);
+                                  return cudaGetLastError();
+                              });
+        }
+    }
     if (!fast) {
         using GL = Layout<T, N, AutoCfg<T, N, MODE>::GR, AutoCfg<T, N, MODE>::GC, MODE>;
         auto kern = lub_invert_kernel<T, N, AutoCfg<T, N, MODE>::GR, AutoCfg<T, N, MODE>::GC, MODE>;
@@ -374,7 +439,7 @@ cudaError_t launch(void* A, int32_t* piv, long long batch, int threads_req, cuda
     // When the TMA path is compiled in but not taken (batch beyond 32-bit tile coordinates, LUB_OPT_STAGING) the fast cache entry
     // would be shared by two kernels: keep a second one.
     static KernelCache cache_fast2[kMaxDevices];
-    KernelCache& cf = TC::ON ? cache_fast2[dev] : cache_fast[dev];
+    KernelCache& cf = (TC::ON || BC::ON) ? cache_fast2[dev] : cache_fast[dev];
     // no pivoting on the 16-byte image: the next tile is prefetched with cp.async while this one is
     // eliminated and the results leave straight from the registers (12-22 % faster, N = 16..24,
     // profiles/r01_tune_prefetch.jsonl); no per-tile block barrier there

@@ -20,6 +20,8 @@ ap.add_argument("--cublas", action="store_true")
 ap.add_argument("--refgpu", action="store_true", help="also time the reference's own kernel rebuilt for sm_100 (oracle/_ref)")
 ap.add_argument("--threads", type=int, default=0)
 ap.add_argument("--out", default="")
+ap.add_argument("--staging", type=int, default=0, help="LUB_OPT_STAGING: 0 = library choice, 1 = LSU staging (no TMA / bulk copies)")
+ap.add_argument("--ab", action="store_true", help="time every size with both staging settings, side by side")
 a = ap.parse_args()
 tdt = torch.float32 if a.dtype == "f32" else torch.float64
 es = 4 if a.dtype == "f32" else 8
@@ -27,6 +29,8 @@ peaks = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 peak = json.load(open(peaks))["hbm_gbs"] if os.path.exists(peaks) else 6650.0
 if a.threads:
     lub.set_num_threads(a.threads)
+if a.staging:
+    lub.set_option("staging", a.staging)
 rows = []
 for n in [int(x) for x in a.ns.split(",")]:
     g = torch.Generator(device="cuda").manual_seed(n)
@@ -42,8 +46,22 @@ for n in [int(x) for x in a.ns.split(",")]:
         torch.cuda.synchronize()
         if i: times.append(e0.elapsed_time(e1))
     ms = min(times)
+    ms_lsu = None
+    if a.ab:
+        lub.set_option("staging", 1)
+        t2 = []
+        for i in range(a.iters + 1):
+            A.copy_(orig)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); lub.lu_batched_inplace(A, None, a.mode); e1.record()
+            torch.cuda.synchronize()
+            if i: t2.append(e0.elapsed_time(e1))
+        lub.set_option("staging", 0)
+        ms_lsu = min(t2)
     row = {"n": n, "ms": ms, "Gmat_s": a.batch / ms / 1e6, "GBps": 2 * n * n * es * a.batch / ms / 1e6}
     row["frac_measured_peak"] = row["GBps"] / peak
+    if ms_lsu is not None:
+        row["ms_lsu_staging"] = ms_lsu
     row["gflops_2n3"] = 2 * n ** 3 * a.batch / ms / 1e6
     if a.cublas:
         C = _lib.cublas_lib()

@@ -6,6 +6,7 @@
 #include "lub_tma2.cuh"
 #include "../../matrixinversion_b200/csrc/lub_dmma.cuh"
 #include "lub_v6.cuh"
+#include "../../matrixinversion_b200/csrc/lub_bulk.cuh"
 
 using namespace lub;
 
@@ -155,6 +156,25 @@ struct VT6 {
     static Variant make(const char* name) { return Variant{name, L::MPW, -(NCW + NPW) * 32, L::SMEM_BYTES, set_attr, launch, occ}; }
 };
 #define VART6(T, N, GR, GC, MODE, NCW, NPW, NB, CREG, PREG, NCG, LA, DBG) VT6<T, N, GR, GC, MODE, NCW, NPW, NB, CREG, PREG, NCG, LA, DBG>::make(#T " N=" #N " " #GR "x" #GC " mode" #MODE " c" #NCW " p" #NPW " nb" #NB " creg" #CREG " preg" #PREG " ncg" #NCG " la" #LA " dbg" #DBG " v6")
+
+// bulk-copy staged kernel (lub_bulk.cuh); OPT: 1 = lean step, 2 = old position-wise search, 4 = one image per warp, 8 = BSYNC, 16 = two-reduction search
+template <typename T, int N, int GR, int GC, int MODE, int MINB, int OPT, int MAXT>
+struct VB {
+    using L = BulkLayout<T, N, GR, GC, MODE>;
+    static constexpr auto kern() { return lub_bulk_kernel<T, N, GR, GC, MODE, MINB, (OPT & 8) != 0, (OPT & ~8), MAXT>; }
+    static void set_attr(int smem) { cudaFuncSetAttribute(kern(), cudaFuncAttributeMaxDynamicSharedMemorySize, smem); }
+    static void launch(void* A, int* piv, long long batch, unsigned blocks, int threads, int smem, cudaStream_t s) {
+        kern()<<<blocks, threads, smem, s>>>((T*)A, piv, batch);
+    }
+    static int occ(int threads, int smem) {
+        int o = 0;
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, kern(), threads, smem);
+        return o;
+    }
+    static int smem_of(int warps) { return L::smem_bytes(warps, (OPT & 4) ? 1 : 2); }
+    static Variant make(const char* name) { return Variant{name, L::MPW, -1000000, MAXT, set_attr, launch, occ, &smem_of}; }
+};
+#define VARB(T, N, GR, GC, MODE, MINB, OPT, MAXT) VB<T, N, GR, GC, MODE, MINB, OPT, MAXT>::make(#T " N=" #N " " #GR "x" #GC " mode" #MODE " minb" #MINB " opt" #OPT " maxt" #MAXT " bulk")
 
 #define VAR5(T, N, GR, GC, MODE, NPW, NCW, NB, PRE) V5<T, N, GR, GC, MODE, NPW, NCW, NB, PRE>::make(#T " N=" #N " " #GR "x" #GC " mode" #MODE " p" #NPW " c" #NCW " nb" #NB " opt" #PRE " v5")
 
