@@ -85,12 +85,9 @@ __device__ __forceinline__ void prepass_rowwise_f32(const float* __restrict__ im
     }
 #pragma unroll
     for (int m = 0; m < MI; ++m) {
-        // every row must have ended on a position of its own (a shared maximum retires two rows at once; NaNs
-        // never hit): one REDUX.OR over the one-hot positions, warp-uniform
-        const float wf = (alive[m] != 0.0f) ? (float)(N - 1) : when[m];
-        const int pos = (int)fminf(wf, 31.0f);
-        constexpr unsigned ALL = (N >= 32) ? 0xffffffffu : ((1u << N) - 1u);
-        const bool ok = __reduce_or_sync(0xffffffffu, (lane < N) ? (1u << pos) : 0u) == ALL;
+        const bool ok = __popc(__ballot_sync(0xffffffffu, alive[m] != 0.0f)) == 1;  // warp-uniform
+        // (the index is clamped: with NaN inputs a retired row can "hit" again on an all-zero step and run past N)
+        const int pos = (alive[m] != 0.0f) ? (N - 1) : (int)fminf(when[m], (float)(N - 1));
         if (ok) {
             if (lane < N) perm0[m * N + pos] = lane;
         } else {
@@ -105,26 +102,60 @@ __device__ __forceinline__ void prepass_rowwise_f32(const float* __restrict__ im
 //                 the tree merges into slot 0: (pb & VM_k) != 0, VM_k a compile-time mask;
 //   pick        = the candidate with the largest |A[r][k]| (un-eliminated entries): one CREDUX;
 //   swap        = the picked row takes position k for good, the row that sat at k takes the picked row's
-//                 position (one REDUX.OR broadcasts it; both lanes XOR their word with hp ^ (1 << k)).
-// (A variant that hands the displaced row its next validity bit with a VOTE.ANY, so that the REDUX.OR leaves the
-// critical path, issued 4 more instructions per step and was 10 % slower on N = 31: the kernel is bound by issue
-// slots, not by this chain's latency -- profiles/r02_tune_bulk.md.)
-// A step with several equal maxima (or an all-zero column, where every lane "hits") leaves two lanes on one
-// position: then the N one-hot words no longer cover N positions once each, and the matrix is redone by the
-// exact search, which also knows the tree's tie order (same rule as the other fast searches).
+//                 position: a REDUX.MAX broadcasts it (one lane contributes), both lanes XOR their word with
+//                 hp ^ (1 << k).  (REDUX.OR / .ADD / .XOR issue every 8-10 cycles on B200, REDUX.MAX / .MIN and
+//                 CREDUX every 2.2: profiles/r02_search_costs.jsonl.)
+// From step KH on the tree reaches every remaining slot (small remaining counts: e.g. N = 18 from step 9), positions
+// no longer matter and the search continues as the plain row-wise one on the FMA pipe (fp32).
+// Ties: a step with several equal maxima (or an all-zero column, where every lane "hits") needs the tree's own
+// order.  Every lane records its hits; unless they add up to one per step and the final positions cover
+// 0..N-1 once each, the matrix is redone by the exact search (same rule as the other fast searches).
+// (A variant that hands the displaced row its next validity bit with a VOTE.ANY, so that the exchange leaves the
+// critical path of a step, issues 4 more instructions per step and measured 9-40 % slower, N = 18..31, before and
+// after the exchange became a CREDUX.MAX -- profiles/r02_tune_bulk.md.)
+constexpr int rowpos_tail_start(int n, int mode) {  // first step from which every later step sees all rows below it
+    if (mode != kModeParallel) return 0;
+    const unsigned all = (n >= 32) ? 0xffffffffu : ((1u << n) - 1u);
+    const unsigned reach = reach_mask_of(n);
+    int k0 = 0;
+    for (int k = 0; k < n - 1; ++k)
+        if ((((reach << (k + 1)) | (1u << k)) & all) != ((all << k) & all)) k0 = k + 1;
+    return k0;
+}
+template <int N, int MODE> struct RowposTail { static constexpr int value = rowpos_tail_start(N, MODE); };
+
+// The picked row and the row at position k (bitk) swap positions.  `acc` collects the position word of this lane at
+// the steps it was picked at -- a plain data dependency per step (a predicated counter makes ptxas defer the
+// additions and rebuild them from predicates it has to spill into a register: four instructions per step).
+__device__ __forceinline__ void rowpos_swap(unsigned& pb, unsigned& acc, bool hit, unsigned bitk) {
+    const unsigned mine = hit ? pb : 0u;
+    const unsigned hp = __reduce_max_sync(0xffffffffu, mine);
+    acc |= mine;
+    // if (hit || pb == bit k) pb ^= hp ^ bit k;
+    asm("{ .reg .pred q, r;\n"
+        "setp.ne.s32 q, %1, 0;\n"
+        "setp.eq.or.u32 r, %0, %2, q;\n"
+        "@r lop3.b32 %0, %0, %3, %2, 0x96;\n}"
+        : "+r"(pb) : "r"((int)hit), "r"(bitk), "r"(hp));
+}
+
 template <typename T, int N, int MODE, int P, int MS, int MI>
 __device__ __forceinline__ void prepass_rowpos(const T* __restrict__ img0, int* __restrict__ perm0,
                                                const int8_t* __restrict__ slot_rank, int lane) {
     using U = typename FpBits<T>::U;
     constexpr unsigned ALL = (N >= 32) ? 0xffffffffu : ((1u << N) - 1u);
     constexpr unsigned REACH = ReachMask<N>::value;
+    constexpr int K0 = RowposTail<N, MODE>::value;
+    // the row-wise tail pays for its switch-over when it covers a few steps; fp64 keeps one code path
+    constexpr int KH = (sizeof(T) == 4 && K0 + 4 <= N - 1) ? K0 : (N - 1);
     const int roff = ((lane < N) ? lane : 0) * P;
-    unsigned pb[MI];
+    unsigned pb[MI], nh[MI];  // nh: the positions this lane was picked from (one bit per hit)
 #pragma unroll
-    for (int m = 0; m < MI; ++m) pb[m] = (lane < N) ? (1u << lane) : 0u;
+    for (int m = 0; m < MI; ++m) { pb[m] = (lane < N) ? (1u << lane) : 0u; nh[m] = 0u; }
 #pragma unroll
-    for (int k = 0; k < N - 1; ++k) {
+    for (int k = 0; k < KH; ++k) {
         const unsigned vmask = ((MODE == kModeParallel) ? ((REACH << (k + 1)) | (1u << k)) : (ALL << k)) & ALL;
+        // (hit is consumed where it is produced: a predicate kept across the MI chains gets spilled into a register)
         if constexpr (sizeof(T) == 4) {
             float v[MI], mx[MI];
 #pragma unroll
@@ -132,12 +163,7 @@ __device__ __forceinline__ void prepass_rowpos(const T* __restrict__ img0, int* 
 #pragma unroll
             for (int m = 0; m < MI; ++m) mx[m] = warp_max_abs(v[m]);
 #pragma unroll
-            for (int m = 0; m < MI; ++m) {
-                const bool hit = fabsf(v[m]) == mx[m];
-                const unsigned hp = __reduce_or_sync(0xffffffffu, hit ? pb[m] : 0u);
-                // the picked row and the row at position k swap places: both XOR with (hp ^ bit k)
-                if (hit || pb[m] == (1u << k)) pb[m] ^= hp ^ (1u << k);
-            }
+            for (int m = 0; m < MI; ++m) rowpos_swap(pb[m], nh[m], fabsf(v[m]) == mx[m], 1u << k);
         } else {
             U v[MI], mx[MI];
 #pragma unroll
@@ -145,20 +171,41 @@ __device__ __forceinline__ void prepass_rowpos(const T* __restrict__ img0, int* 
 #pragma unroll
             for (int m = 0; m < MI; ++m) mx[m] = warp_max_bits(v[m]);
 #pragma unroll
+            for (int m = 0; m < MI; ++m) rowpos_swap(pb[m], nh[m], v[m] == mx[m], 1u << k);
+        }
+    }
+    float alive[MI], when[MI];
+    if constexpr (KH < N - 1) {
+#pragma unroll
+        for (int m = 0; m < MI; ++m) { alive[m] = ((pb[m] & ((ALL << KH) & ALL)) != 0u) ? 1.0f : 0.0f; when[m] = 0.0f; }
+#pragma unroll
+        for (int k = KH; k < N - 1; ++k) {
+            float v[MI], mx[MI];
+#pragma unroll
+            for (int m = 0; m < MI; ++m) v[m] = (float)img0[m * MS + roff + k] * alive[m];
+#pragma unroll
+            for (int m = 0; m < MI; ++m) mx[m] = warp_max_abs(v[m]);
+#pragma unroll
             for (int m = 0; m < MI; ++m) {
-                const bool hit = v[m] == mx[m];
-                const unsigned hp = __reduce_or_sync(0xffffffffu, hit ? pb[m] : 0u);
-                // the picked row and the row at position k swap places: both XOR with (hp ^ bit k)
-                if (hit || pb[m] == (1u << k)) pb[m] ^= hp ^ (1u << k);
+                const float h = (fabsf(v[m]) == mx[m]) ? 1.0f : 0.0f;
+                when[m] = fmaf(h, (float)k, when[m]);
+                alive[m] = fmaf(-h, alive[m], alive[m]);
             }
         }
     }
 #pragma unroll
     for (int m = 0; m < MI; ++m) {
-        const unsigned cover = __reduce_or_sync(0xffffffffu, pb[m]);
-        const unsigned odd = __ballot_sync(0xffffffffu, __popc(pb[m]) != ((lane < N) ? 1 : 0));
-        if (cover == ALL && odd == 0u) {  // warp-uniform: every row on one position, every position taken
-            if (lane < N) perm0[m * N + (__ffs((int)pb[m]) - 1)] = lane;
+        int pos = __ffs((int)pb[m]) - 1;  // rows picked by the position-aware steps (and, without a tail, the last row)
+        if constexpr (KH < N - 1) {
+            const bool late = (pb[m] & ((ALL << KH) & ALL)) != 0u;
+            if (late) pos = (alive[m] != 0.0f) ? (N - 1) : (int)fminf(when[m], 31.0f);
+        }
+        const unsigned bit = (lane < N && pos >= 0) ? (1u << pos) : 0u;
+        const unsigned cover = __reduce_or_sync(0xffffffffu, bit);
+        const int hits = (int)__reduce_add_sync(0xffffffffu, (unsigned)__popc(nh[m]));
+        const unsigned odd = __ballot_sync(0xffffffffu, (lane < N) && __popc(pb[m]) != 1);
+        if (cover == ALL && hits == KH && odd == 0u) {  // warp-uniform
+            if (lane < N) perm0[m * N + pos] = lane;
         } else {
             prepass_exact<T, N, MODE, P>(img0 + m * MS, perm0 + m * N, slot_rank, lane);
         }
@@ -192,6 +239,9 @@ lub_bulk_kernel(T* __restrict__ A, int32_t* __restrict__ piv, long long batch) {
 
     if (MODE == kModeParallel && threadIdx.x < N) slot_rank[threadIdx.x] = (int8_t)tree_slot_rank(threadIdx.x, N);
     if (lane == 0) { mbar_init(bar0, 1); mbar_init(bar0 + 1, 1); }
+    // every entry of perm[] is a row index from the start: a search that NaN inputs derail may skip entries, never invent one
+    if (MODE != kModeNone)
+        for (int x = lane; x < MPW * N; x += 32) perm_all[x] = x % N;
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     __syncthreads();
 
@@ -275,7 +325,7 @@ lub_bulk_kernel(T* __restrict__ A, int32_t* __restrict__ piv, long long batch) {
             const int i = li * GR + gr;
             const bool rok = (li * GR + GR - 1 < N) || (i < N);
             int prow = rok ? i : 0;
-            if (MODE != kModeNone) prow = rok ? min((unsigned)perm[i], (unsigned)(N - 1)) : 0;  // clamped: NaN inputs stay memory-safe
+            if (MODE != kModeNone) prow = rok ? perm[i] : 0;
             const T* rowp = mimg + prow * P;
 #pragma unroll
             for (int q = 0; q < CPL; ++q) {
@@ -327,7 +377,7 @@ lub_bulk_kernel(T* __restrict__ A, int32_t* __restrict__ piv, long long batch) {
 #pragma unroll
             for (int lj = 0; lj < LC; ++lj) {
                 const int j = gc * LC + lj;
-                pcol[lj] = ((GC * LC <= N) || (j < N)) ? (int)min((unsigned)perm[j], (unsigned)(N - 1)) : -1;
+                pcol[lj] = ((GC * LC <= N) || (j < N)) ? perm[j] : -1;
             }
             __syncwarp();  // all lanes hold their blocks and columns: the image may be overwritten
 #pragma unroll

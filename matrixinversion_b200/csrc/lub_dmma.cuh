@@ -164,6 +164,7 @@ lub_dmma_kernel(const __grid_constant__ CUtensorMap tmap, double* __restrict__ A
 
     if (MODE == kModeParallel && threadIdx.x < N) slot_rank[threadIdx.x] = (int8_t)tree_slot_rank(threadIdx.x, N);
     if (lane == 0) mbar_init(bar, 1);
+    if (MODE != kModeNone) perm[lane] = lane;  // always row indices, whatever a search derailed by NaN inputs leaves unwritten
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     __syncthreads();
 

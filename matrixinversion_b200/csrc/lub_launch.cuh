@@ -150,6 +150,71 @@ struct V3Cfg {
 #endif
 constexpr bool kUseTma = LUB_USE_TMA != 0;
 
+// Which configurations run the bulk-copy staged kernel (lub_bulk.cuh): the sizes whose rows are not 16-byte
+// multiples, i.e. the ones a tensor map cannot describe.  Lane grid as pick_v3_cfg, with the vector width the
+// dense image allows; two images per warp, so the block shape follows from shared memory: two (three, four for
+// small N) 256-thread blocks per SM where they fit, else one 384-thread block.
+constexpr Cfg pick_bulk_cfg(int n, int es) {
+    const int epv = 16 / es;
+    const int ch = (n % epv == 0) ? epv : ((epv == 4 && n % 2 == 0) ? 2 : 1);
+    const int cpr = n / ch;
+    const int budget = (es == 4) ? 64 : 36;
+    for (int g = 1; g <= 32; g *= 2) {
+        if (g == 2) continue;
+        int best_cost = 1 << 30;
+        Cfg best{0, 0};
+        for (int gr = 1; gr <= g; gr *= 2) {
+            const int gc = g / gr;
+            const int lr = cdiv(n, gr), lc = cdiv(cpr, gc) * ch;
+            if (lr * lc > budget) continue;
+            const int cost = 64 * ((gc > 1 ? lr : 0) + (gr > 1 ? lc : 0)) + lr;
+            if (cost < best_cost) { best_cost = cost; best = Cfg{gr, gc}; }
+        }
+        if (best.gr) return best;
+    }
+    return Cfg{4, 8};
+}
+struct BulkChoice { bool on; int gr, gc, minb, maxt, threads, opt; };
+#ifndef LUB_BULK_MIN_N
+#define LUB_BULK_MIN_N 5
+#endif
+#ifndef LUB_BULK_PAR4
+#define LUB_BULK_PAR4 1
+#endif
+constexpr BulkChoice pick_bulk(int n, int es, int mode) {
+    const Cfg c = pick_bulk_cfg(n, es);
+    // fp32: the sizes without 16-byte rows; fp64: every size but the two TMA / DMMA ones (N = 16, 32) -- there the
+    // bulk-staged block layout also beats the rolled-step kernel of lub_v4.cuh (N = 31: 7.7 -> 5.8 ms without pivoting)
+    // (fp64 exceptions, measured slower: profiles/r02_bulk_ab_f64_*.json)
+    const bool f64_off = n == 16 || n == 32 || n == 8 || (mode == kModeNone && (n == 13 || n == 18 || n == 20)) ||
+                         (mode != kModeNone && n == 9) || (mode == kModeParallel && n == 20);
+    // fp32 parallel pivoting at N = 12, 20, 24, 28: the position-aware row-wise search on the dense image
+    const bool f32_par4 = LUB_BULK_PAR4 && mode == kModeParallel && (n == 12 || n == 20 || n == 24 || n == 28);
+    const bool on = n >= LUB_BULK_MIN_N && ((es == 4) ? (n % 4 != 0 || f32_par4) : !f64_off);
+    if (!on) return BulkChoice{false, c.gr, c.gc, 1, kMaxThreads, 256, 0};
+    const int mpw = 32 / (c.gr * c.gc);
+    const int img = (mpw * n * n * es + 15) / 16 * 16 + 16;
+    const int perm = (mode != kModeNone) ? (mpw * n * 4 + 15) / 16 * 16 : 0;
+    const int wb = 2 * img + perm + 16;
+    int minb = pick_minb(n, es, mode != kModeNone);
+    while (minb > 1 && minb * (64 + 8 * wb + 1024) > 233472) --minb;
+    // measured (profiles/r02_tune_bulk.md): the lean elimination step pays from N = 25 on (+-1 % below, -8 % at N = 18
+    // without pivoting); one lane per matrix (N <= 8) searches its own matrix, larger groups search warp-wide
+    // (N = 15 serial: 0.52 vs 0.87 ms); from N = 25 on (two matrices per warp, 8 x 8 blocks) one 384-thread block per SM
+    // with 168 registers beats two 256-thread blocks with 128 (N = 27: 1.53 vs 1.67 ms without pivoting, 2.36 vs 2.49
+    // parallel); fp64 needs the 168 registers from N = 21 on (6 x 6 doubles per lane: 2.11 vs 2.82 ms)
+    const int opt = ((es == 4 && n >= 25) ? kBulkLean : 0) | (n <= 8 ? kBulkGroupSearch : 0);
+    const bool big = (es == 4) ? (n >= 25) : (n >= 21);
+    if (minb == 1 || big) return BulkChoice{true, c.gr, c.gc, 1, 384, 384, opt};
+    return BulkChoice{true, c.gr, c.gc, minb, kMaxThreads, 256, opt};
+}
+template <typename T, int N, int MODE>
+struct BulkCfg {
+    static constexpr BulkChoice c = pick_bulk(N, (int)sizeof(T), MODE);
+    static constexpr bool ON = kUseTma && c.on;
+    static constexpr int GR = c.gr, GC = c.gc, MINB = c.minb, MAXT = c.maxt, THREADS = c.threads, OPT = c.opt;
+};
+
 // Which configurations run the TMA-staged kernel (lub_tma.cuh), on which lane grid and with or without
 // the per-tile block barrier.  Measured choices (profiles/r01_tune_tma.jsonl, r01_tune_late.jsonl):
 //   * rows of one 128-byte line (N = 32 fp32, N = 16 fp64): every mode, the v3 lane grid;
@@ -182,58 +247,10 @@ constexpr TmaChoice pick_tma(int n, int es, int mode, Cfg v3) {
 template <typename T, int N, int MODE>
 struct TmaCfg {
     static constexpr TmaChoice c = pick_tma(N, (int)sizeof(T), MODE, Cfg{V3Cfg<T, N, MODE>::GR, V3Cfg<T, N, MODE>::GC});
-    static constexpr bool ON = kUseTma && c.on;
+    static constexpr bool ON = kUseTma && c.on && !pick_bulk(N, (int)sizeof(T), MODE).on;
     static constexpr int GR = c.gr, GC = c.gc;
     static constexpr bool BSYNC = c.bsync;
     static constexpr int OPT = c.opt, MAXT = c.maxt, THREADS = c.threads;
-};
-
-// Which configurations run the bulk-copy staged kernel (lub_bulk.cuh): the sizes whose rows are not 16-byte
-// multiples, i.e. the ones a tensor map cannot describe.  Lane grid as pick_v3_cfg, with the vector width the
-// dense image allows; two images per warp, so the block shape follows from shared memory: two (three, four for
-// small N) 256-thread blocks per SM where they fit, else one 384-thread block.
-constexpr Cfg pick_bulk_cfg(int n, int es) {
-    const int epv = 16 / es;
-    const int ch = (n % epv == 0) ? epv : ((epv == 4 && n % 2 == 0) ? 2 : 1);
-    const int cpr = n / ch;
-    const int budget = (es == 4) ? 64 : 36;
-    for (int g = 1; g <= 32; g *= 2) {
-        if (g == 2) continue;
-        int best_cost = 1 << 30;
-        Cfg best{0, 0};
-        for (int gr = 1; gr <= g; gr *= 2) {
-            const int gc = g / gr;
-            const int lr = cdiv(n, gr), lc = cdiv(cpr, gc) * ch;
-            if (lr * lc > budget) continue;
-            const int cost = 64 * ((gc > 1 ? lr : 0) + (gr > 1 ? lc : 0)) + lr;
-            if (cost < best_cost) { best_cost = cost; best = Cfg{gr, gc}; }
-        }
-        if (best.gr) return best;
-    }
-    return Cfg{4, 8};
-}
-struct BulkChoice { bool on; int gr, gc, minb, maxt, threads, opt; };
-#ifndef LUB_BULK_MIN_N
-#define LUB_BULK_MIN_N 5
-#endif
-constexpr BulkChoice pick_bulk(int n, int es, int mode) {
-    const Cfg c = pick_bulk_cfg(n, es);
-    if (es != 4 || n % 4 == 0 || n < LUB_BULK_MIN_N) return BulkChoice{false, c.gr, c.gc, 1, kMaxThreads, 256, 0};
-    const int mpw = 32 / (c.gr * c.gc);
-    const int img = (mpw * n * n * es + 15) / 16 * 16 + 16;
-    const int perm = (mode != kModeNone) ? (mpw * n * 4 + 15) / 16 * 16 : 0;
-    const int wb = 2 * img + perm + 16;
-    int minb = pick_minb(n, es, mode != kModeNone);
-    while (minb > 1 && minb * (64 + 8 * wb + 1024) > 233472) --minb;
-    const int opt = (n >= 25 ? kBulkLean : 0) | (n <= 16 ? kBulkGroupSearch : 0);
-    if (minb == 1) return BulkChoice{true, c.gr, c.gc, 1, 384, 384, opt};
-    return BulkChoice{true, c.gr, c.gc, minb, kMaxThreads, 256, opt};
-}
-template <typename T, int N, int MODE>
-struct BulkCfg {
-    static constexpr BulkChoice c = pick_bulk(N, (int)sizeof(T), MODE);
-    static constexpr bool ON = kUseTma && c.on;
-    static constexpr int GR = c.gr, GC = c.gc, MINB = c.minb, MAXT = c.maxt, THREADS = c.threads, OPT = c.opt;
 };
 
 constexpr int kMaxDevices = 64;

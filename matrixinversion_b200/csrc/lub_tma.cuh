@@ -211,8 +211,10 @@ __device__ __forceinline__ void prepass_rowwise_swz(const unsigned char* img, in
 #pragma unroll
         for (int m = 0; m < MI; ++m) {
             const bool ok = __popc(__ballot_sync(0xffffffffu, alive[m] != 0.0f)) == 1;  // warp-uniform
+            // (the index is clamped: with NaN inputs a retired row can "hit" again on an all-zero step and run past N)
+            const int pos = (alive[m] != 0.0f) ? (N - 1) : (int)fminf(when[m], (float)(N - 1));
             if (ok) {
-                if (lane < N) perm0[m * N + ((alive[m] != 0.0f) ? (N - 1) : (int)when[m])] = lane;
+                if (lane < N) perm0[m * N + pos] = lane;
             } else {
                 prepass_exact_swz<T, N, MODE>(img, row0 + m * N, perm0 + m * N, slot_rank, lane);
             }
@@ -357,6 +359,9 @@ lub_tma_kernel(const __grid_constant__ CUtensorMap tmap, T* __restrict__ A, int3
 
     if (MODE == kModeParallel && threadIdx.x < N) slot_rank[threadIdx.x] = (int8_t)tree_slot_rank(threadIdx.x, N);
     if (lane == 0) { mbar_init(bar0, 1); mbar_init(bar0 + 1, 1); }
+    // every entry of perm[] is a row index from the start: a search that NaN inputs derail may skip entries, never invent one
+    if (MODE != kModeNone)
+        for (int x = lane; x < MPW * N; x += 32) perm_all[x] = x % N;
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     __syncthreads();
 

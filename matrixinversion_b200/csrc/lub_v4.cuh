@@ -139,6 +139,11 @@ lub_v4_kernel(T* __restrict__ A, int32_t* __restrict__ piv, long long batch) {
         if (threadIdx.x < N) slot_rank[threadIdx.x] = (int8_t)tree_slot_rank(threadIdx.x, N);
         __syncthreads();
     }
+    // every entry of perm[] is a row index from the start: a search that NaN inputs derail may skip entries, never invent one
+    if (MODE != kModeNone) {
+        for (int x = threadIdx.x & 31; x < MPW * N; x += 32) perm_all[x] = x % N;
+        __syncwarp();
+    }
 
     const int g = lane % G;
     const int ml = lane / G;

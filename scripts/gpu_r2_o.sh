@@ -1,6 +1,14 @@
 #!/bin/bash
 mkdir -p gpurun_out
-python scripts/tune/run.py --threads 256 --iters 3 > gpurun_out/o_tune_dmma.jsonl 2> gpurun_out/o_tune_dmma.err
-cat gpurun_out/o_tune_dmma.jsonl
-ncu --set full --clock-control none --import-source on -k regex:lub_dmma -s 1 -c 1 -f -o gpurun_out/o_dmma_mode2 python scripts/tune/run.py --threads 256 --iters 1 --only mode2 > gpurun_out/o_ncu.log 2>&1
-tail -2 gpurun_out/o_ncu.log
+timeout 600 python -m pytest tests/test_gpu_parity.py -m gpu -x -q > gpurun_out/o_pytest.log 2>&1
+tail -3 gpurun_out/o_pytest.log
+cd scripts/tune
+timeout 600 python run.py --threads 256,384 --only bulk --iters 4 > ../../gpurun_out/o_tune_bulk.jsonl 2> ../../gpurun_out/o_tune_bulk.err
+tail -3 ../../gpurun_out/o_tune_bulk.err
+cd ../..
+python - <<'PY'
+import json
+for l in open("gpurun_out/o_tune_bulk.jsonl"):
+    d=json.loads(l)
+    if d.get("ok"): print(d["variant"], d["threads"], d["ms"], "occ", d["occ_blocks"], d["piv_equal"], d["values_close"], d["matrices_differing_1e-6"])
+PY

@@ -256,6 +256,60 @@ def test_tma_paths_ragged_batches_leave_neighbours_alone():
                 assert np.array_equal(gp[:B], pfull[:B]) and np.all(gp[B:] == -1), (n, dtype, mode, B)
 
 
+def test_bulk_copy_paths_ragged_batches_and_lsu_staging_agree():
+    """The bulk-copy staged configurations (csrc/lub_bulk.cuh: rows that are not 16-byte multiples -- tile spans that start 4,
+    8 or 12 bytes off a 16-byte boundary, ragged ends) on batch sizes that end inside a warp tile: head and tail words leave
+    by plain stores, the interior by one cp.async.bulk; the matrices after the batch (a guard region in the same allocation)
+    and the pivot rows after it stay untouched; results equal the full-batch run and -- same arithmetic, other staging --
+    the LSU-staged kernels (LUB_OPT_STAGING = 1) bit for bit."""
+    guard = 5
+    cases = ((5, np.float32), (7, np.float32), (13, np.float32), (18, np.float32), (22, np.float32), (27, np.float32), (31, np.float32),
+             (12, np.float32), (28, np.float32), (7, np.float64), (19, np.float64), (26, np.float64), (31, np.float64))
+    for n, dtype in cases:
+        for mode in MODES:
+            if n % 4 == 0 and dtype == np.float32 and mode != 2:
+                continue  # fp32 multiples of 4 take this path with parallel pivoting only
+            assert lub.kernel_name(n, mode, dtype) == "lub_bulk_kernel", (n, dtype, mode)
+            A = synthetic(n, 203 + guard, dtype, dominant=(mode == 0))
+            Xfull, pfull = gpu_invert(A, mode)
+            lub.set_option("staging", 1)
+            try:
+                assert lub.kernel_name(n, mode, dtype) != "lub_bulk_kernel"
+                Xlsu, plsu = gpu_invert(A, mode)
+            finally:
+                lub.set_option("staging", 0)
+            assert np.array_equal(pfull, plsu), (n, dtype, mode)
+            assert np.array_equal(Xfull, Xlsu, equal_nan=True), (n, dtype, mode)
+            for B in (1, 2, 3, 4, 5, 9, 33, 203):
+                base = torch.from_numpy(A[: B + guard].copy()).cuda()
+                piv = torch.full((B + guard, n), -1, dtype=torch.int32, device="cuda")
+                lub.lu_batched_inplace(base[:B], piv[:B], mode)
+                torch.cuda.synchronize()
+                got = base.cpu().numpy()
+                assert np.array_equal(got[:B], Xfull[:B], equal_nan=True), (n, dtype, mode, B)
+                assert np.array_equal(got[B:], A[B : B + guard]), ("guard overwritten", n, dtype, mode, B)
+                gp = piv.cpu().numpy()
+                assert np.array_equal(gp[:B], pfull[:B]) and np.all(gp[B:] == -1), (n, dtype, mode, B)
+
+
+def test_nan_inputs_stay_memory_safe():
+    """NaN / inf inputs are outside the numerical contract (DESIGN (e)) but must not fault: the pivot searches may leave a
+    permutation that is not one, so the kernels clamp every row index they read back."""
+    rng = np.random.default_rng(5)
+    for n, dtype in ((31, np.float32), (18, np.float32), (32, np.float32), (19, np.float64)):
+        A = rng.random((257, n, n)).astype(dtype)
+        A[::3, :, 0] = np.nan
+        A[1::7] = np.nan
+        A[2::11, 3, :] = np.inf
+        for mode in (1, 2):
+            X, piv = gpu_invert(A, mode)
+            torch.cuda.synchronize()
+            assert piv.min() >= 0 and piv.max() < n, (n, dtype, mode)   # whatever the order, they are row indices
+        ok = np.isfinite(A).all(axis=(1, 2))
+        Xc, pc = gpu_invert(A[ok], 2)
+        assert np.array_equal(pc, gpu_invert(A, 2)[1][ok])    # clean matrices are unaffected by their neighbours
+
+
 @pytest.mark.parametrize("dtype", [np.float32, np.float64])
 def test_lu_only_factors(dtype):
     """lu_batched_factor_inplace: permutation vectors bit-exact vs the oracle's
