@@ -142,7 +142,6 @@ __device__ __forceinline__ void rowpos_swap(unsigned& pb, unsigned& acc, bool hi
 template <typename T, int N, int MODE, int P, int MS, int MI>
 __device__ __forceinline__ void prepass_rowpos(const T* __restrict__ img0, int* __restrict__ perm0,
                                                const int8_t* __restrict__ slot_rank, int lane) {
-    using U = typename FpBits<T>::U;
     constexpr unsigned ALL = (N >= 32) ? 0xffffffffu : ((1u << N) - 1u);
     constexpr unsigned REACH = ReachMask<N>::value;
     constexpr int K0 = RowposTail<N, MODE>::value;
@@ -165,11 +164,11 @@ __device__ __forceinline__ void prepass_rowpos(const T* __restrict__ img0, int* 
 #pragma unroll
             for (int m = 0; m < MI; ++m) rowpos_swap(pb[m], nh[m], fabsf(v[m]) == mx[m], 1u << k);
         } else {
-            U v[MI], mx[MI];
+            uint32_t v[MI], mx[MI];  // fp64: the upper word of |x| (FpBits<double>::hi31); equal upper words are a tie
 #pragma unroll
-            for (int m = 0; m < MI; ++m) v[m] = ((pb[m] & vmask) != 0u) ? FpBits<T>::absbits(img0[m * MS + roff + k]) : U(0);
+            for (int m = 0; m < MI; ++m) v[m] = ((pb[m] & vmask) != 0u) ? FpBits<T>::hi31(img0[m * MS + roff + k]) : 0u;
 #pragma unroll
-            for (int m = 0; m < MI; ++m) mx[m] = warp_max_bits(v[m]);
+            for (int m = 0; m < MI; ++m) mx[m] = __reduce_max_sync(0xffffffffu, v[m]);
 #pragma unroll
             for (int m = 0; m < MI; ++m) rowpos_swap(pb[m], nh[m], v[m] == mx[m], 1u << k);
         }

@@ -208,7 +208,7 @@ template <int N, int MODE> struct RowwiseOk { static constexpr bool value = roww
 template <typename T, int N, int MODE, int P, int MI, bool INLINE_EXACT, bool VEC = false>
 __device__ __forceinline__ void prepass_rowwise(const T* const (&img)[MI], int* const (&perm)[MI],
                                                 const int8_t* __restrict__ slot_rank, int lane) {
-    using U = typename FpBits<T>::U;
+    using U = uint32_t;  // keys: the upper word of |x| (fp64: see FpBits<double>::hi31 -- one REDUX per step)
     const int roff = ((lane < N) ? lane : 0) * P;
     U alive[MI];
     int when[MI];
@@ -226,10 +226,10 @@ __device__ __forceinline__ void prepass_rowwise(const T* const (&img)[MI], int* 
 #pragma unroll
         for (int m = 0; m < MI; ++m) {
             const T xv = VEC ? x[m][k % EPV] : img[m][roff + k];
-            key[m] = ((FpBits<T>::absbits(xv) << 1) | U(1)) & alive[m];
+            key[m] = ((FpBits<T>::hi31(xv) << 1) | U(1)) & alive[m];
         }
 #pragma unroll
-        for (int m = 0; m < MI; ++m) mx[m] = warp_max_bits(key[m]);
+        for (int m = 0; m < MI; ++m) mx[m] = __reduce_max_sync(0xffffffffu, key[m]);
 #pragma unroll
         for (int m = 0; m < MI; ++m) {
             const bool hit = key[m] == mx[m];

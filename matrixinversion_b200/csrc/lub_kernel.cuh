@@ -39,12 +39,17 @@ template <typename T> struct FpBits;
 template <> struct FpBits<float> {
     using U = uint32_t;
     static __device__ __forceinline__ U absbits(float x) { return __float_as_uint(x) & 0x7fffffffu; }
+    static __device__ __forceinline__ uint32_t hi31(float x) { return absbits(x); }
 };
 template <> struct FpBits<double> {
     using U = unsigned long long;
     static __device__ __forceinline__ U absbits(double x) {
         return (unsigned long long)__double_as_longlong(x) & 0x7fffffffffffffffull;
     }
+    // the upper word of |x|: orders like |x| wherever two values differ in their upper 32 bits.  The fast pivot
+    // searches compare these (ONE warp reduction per step instead of two); two candidates that agree in the upper
+    // word look like a tie to them, and every tie is redone by the exact 64-bit search.
+    static __device__ __forceinline__ uint32_t hi31(double x) { return (uint32_t)__double2hiint(x) & 0x7fffffffu; }
 };
 
 // |v| compared through its bit pattern: identical to the reference's `fabs(a) > fabs(b)`

@@ -154,7 +154,10 @@ constexpr bool kUseTma = LUB_USE_TMA != 0;
 // multiples, i.e. the ones a tensor map cannot describe.  Lane grid as pick_v3_cfg, with the vector width the
 // dense image allows; two images per warp, so the block shape follows from shared memory: two (three, four for
 // small N) 256-thread blocks per SM where they fit, else one 384-thread block.
-constexpr Cfg pick_bulk_cfg(int n, int es) {
+constexpr Cfg pick_bulk_cfg(int n, int es, int mode = kModeParallel) {
+    // fp64 without pivoting, N = 25..30: 16 lanes per matrix (7 x 7 / 8 x 8 doubles per lane, 255 registers, one 256-thread
+    // block per SM) halve the shuffles per matrix: -5..-12 % against the 32-lane grid (profiles/r02_tune_bulk.md)
+    if (es == 8 && mode == kModeNone && n >= 25 && n <= 30) return Cfg{4, 4};
     const int epv = 16 / es;
     const int ch = (n % epv == 0) ? epv : ((epv == 4 && n % 2 == 0) ? 2 : 1);
     const int cpr = n / ch;
@@ -178,16 +181,19 @@ struct BulkChoice { bool on; int gr, gc, minb, maxt, threads, opt; };
 #ifndef LUB_BULK_MIN_N
 #define LUB_BULK_MIN_N 5
 #endif
+#ifndef LUB_BULK_F64_EXC
+#define LUB_BULK_F64_EXC 1
+#endif
 #ifndef LUB_BULK_PAR4
 #define LUB_BULK_PAR4 1
 #endif
 constexpr BulkChoice pick_bulk(int n, int es, int mode) {
-    const Cfg c = pick_bulk_cfg(n, es);
+    const Cfg c = pick_bulk_cfg(n, es, mode);
     // fp32: the sizes without 16-byte rows; fp64: every size but the two TMA / DMMA ones (N = 16, 32) -- there the
     // bulk-staged block layout also beats the rolled-step kernel of lub_v4.cuh (N = 31: 7.7 -> 5.8 ms without pivoting)
     // (fp64 exceptions, measured slower: profiles/r02_bulk_ab_f64_*.json)
-    const bool f64_off = n == 16 || n == 32 || n == 8 || (mode == kModeNone && (n == 13 || n == 18 || n == 20)) ||
-                         (mode != kModeNone && n == 9) || (mode == kModeParallel && n == 20);
+    const bool f64_off = n == 16 || n == 32 || (LUB_BULK_F64_EXC && (n == 8 || (mode == kModeNone && (n == 13 || n == 18 || n == 20)) ||
+                         (mode == kModeSerial && n == 20)));
     // fp32 parallel pivoting at N = 12, 20, 24, 28: the position-aware row-wise search on the dense image
     const bool f32_par4 = LUB_BULK_PAR4 && mode == kModeParallel && (n == 12 || n == 20 || n == 24 || n == 28);
     const bool on = n >= LUB_BULK_MIN_N && ((es == 4) ? (n % 4 != 0 || f32_par4) : !f64_off);
@@ -205,6 +211,7 @@ constexpr BulkChoice pick_bulk(int n, int es, int mode) {
     // parallel); fp64 needs the 168 registers from N = 21 on (6 x 6 doubles per lane: 2.11 vs 2.82 ms)
     const int opt = ((es == 4 && n >= 25) ? kBulkLean : 0) | (n <= 8 ? kBulkGroupSearch : 0);
     const bool big = (es == 4) ? (n >= 25) : (n >= 21);
+    if (es == 8 && mode == kModeNone && n >= 25 && n <= 30) return BulkChoice{true, c.gr, c.gc, 1, kMaxThreads, 256, opt};
     if (minb == 1 || big) return BulkChoice{true, c.gr, c.gc, 1, 384, 384, opt};
     return BulkChoice{true, c.gr, c.gc, minb, kMaxThreads, 256, opt};
 }

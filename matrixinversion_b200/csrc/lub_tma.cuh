@@ -220,10 +220,11 @@ __device__ __forceinline__ void prepass_rowwise_swz(const unsigned char* img, in
             }
         }
     } else {
-        U alive[MI];
+        // integer keys: the upper word of |x| (fp64: FpBits<double>::hi31 -- one REDUX per step; equal upper words are a tie)
+        uint32_t alive[MI];
         int when[MI];
 #pragma unroll
-        for (int m = 0; m < MI; ++m) { alive[m] = (lane < N) ? ~U(0) : U(0); when[m] = N - 1; }
+        for (int m = 0; m < MI; ++m) { alive[m] = (lane < N) ? ~0u : 0u; when[m] = N - 1; }
 #pragma unroll
         for (int k = 0; k < N - 1; ++k) {
             if ((k % EPV) == 0) {
@@ -231,21 +232,21 @@ __device__ __forceinline__ void prepass_rowwise_swz(const unsigned char* img, in
                 for (int m = 0; m < MI; ++m)
                     ld_vec<T, EPV>(reinterpret_cast<const T*>(img + swz_byte<RB>(row0 + m * N + row, (k / EPV) << 4)), x[m]);
             }
-            U key[MI], mx[MI];
+            uint32_t key[MI], mx[MI];
 #pragma unroll
-            for (int m = 0; m < MI; ++m) key[m] = ((FpBits<T>::absbits(x[m][k % EPV]) << 1) | U(1)) & alive[m];
+            for (int m = 0; m < MI; ++m) key[m] = ((FpBits<T>::hi31(x[m][k % EPV]) << 1) | 1u) & alive[m];
 #pragma unroll
-            for (int m = 0; m < MI; ++m) mx[m] = warp_max_bits(key[m]);
+            for (int m = 0; m < MI; ++m) mx[m] = __reduce_max_sync(0xffffffffu, key[m]);
 #pragma unroll
             for (int m = 0; m < MI; ++m) {
                 const bool hit = key[m] == mx[m];
                 when[m] = hit ? k : when[m];
-                alive[m] = hit ? U(0) : alive[m];
+                alive[m] = hit ? 0u : alive[m];
             }
         }
 #pragma unroll
         for (int m = 0; m < MI; ++m) {
-            const bool ok = __popc(__ballot_sync(0xffffffffu, alive[m] != U(0))) == 1;  // warp-uniform
+            const bool ok = __popc(__ballot_sync(0xffffffffu, alive[m] != 0u)) == 1;  // warp-uniform
             if (ok) {
                 if (lane < N) perm0[m * N + when[m]] = lane;
             } else {

@@ -2,12 +2,12 @@
 # round 2: systematic tuning run of the bulk-copy staged kernel (scripts/tune/gen_bulk_variants.py)
 mkdir -p gpurun_out
 cd scripts/tune
-timeout 1200 python run.py --threads 256,384 --only bulk --iters 4 > ../../gpurun_out/t5_tune_vote.jsonl 2> ../../gpurun_out/t5_tune_vote.err
-tail -3 ../../gpurun_out/t5_tune_vote.err
+timeout 1200 python run.py --threads 256,384 --only bulk --iters 4 > ../../gpurun_out/t9_tune_f64_44s.jsonl 2> ../../gpurun_out/t9_tune_f64_44s.err
+tail -3 ../../gpurun_out/t9_tune_f64_44s.err
 cd ../..
 python - <<'PY'
 import json
-for l in open("gpurun_out/t5_tune_vote.jsonl"):
+for l in open("gpurun_out/t9_tune_f64_44s.jsonl"):
     d=json.loads(l)
     if d.get("ok"): print(d["variant"], d["threads"], d["ms"], "occ", d["occ_blocks"], d["piv_equal"], d["values_close"], d["matrices_differing_1e-6"])
 PY
