@@ -2,6 +2,7 @@
 // dtype.  Compile with -DLUB_T=float|double -DLUB_TN=f32|f64.
 #include "lub_launch.cuh"
 #include "lub_lapack.cuh"
+#include "lub_lapack2.cuh"
 
 namespace lub {
 
@@ -13,9 +14,30 @@ static cudaError_t launch_lapack_n(void* A, int32_t* ipiv, int32_t* info, long l
     cudaError_t err = cudaGetDevice(&dev);
     if (err != cudaSuccess) return err;
     if (dev < 0 || dev >= kMaxDevices) return cudaErrorInvalidDevice;
+    LaunchCtx x{batch, threads_req > 0 ? threads_req : 256, stream, li, (flags & kLaunchDryRun) != 0, ev0, dev};
+    // N >= 17: the 2-D lane grid with bulk-copy staging (lub_lapack2.cuh) -- 13 instead of N shuffles per step; needs a
+    // 16-byte aligned batch like every bulk / TMA path.  LUB_OPT_STAGING = 1 keeps the lane = row kernel.
+    // (measured, profiles/r02_mode3_grid.jsonl: fp64 1.1-1.6x faster from N = 17 on -- N = 32: 31.7 -> 21.2 ms; fp32 only at N = 32,
+    // 10.6 -> 9.6 ms: below that the lane = row kernel's N fp32 shuffles per step cost less than the 160 instructions per step
+    // this one issues for its position bookkeeping and run-time register selects)
+    if constexpr (N >= 17 && (sizeof(T) == 8 || N == 32)) {
+        if ((x.dry_run || reinterpret_cast<uintptr_t>(A) % 16 == 0) && !(flags & kLaunchNoTma)) {
+            using L2 = Lapack2Layout<T, N>;
+            constexpr int MAXT2 = (sizeof(T) == 4) ? kMaxThreads : 384, MINB2 = (sizeof(T) == 4) ? 2 : 1;
+            static KernelCache cache2[kMaxDevices];
+            auto kern2 = lub_lapack2_kernel<T, N, LUONLY, MAXT2, MINB2>;
+            if (threads_req <= 0) x.threads = MAXT2;
+            return run_kernel(kern2, cache2[dev], x, MAXT2, [](int w) { return L2::smem_bytes(w); }, 1, 32,
+                              LUONLY ? "lub_lapack2_kernel<LUONLY>" : "lub_lapack2_kernel", [&](unsigned blocks, int smem) {
+                                  cudaError_t e = ev0 ? cudaEventRecord(ev0, stream) : cudaSuccess;
+                                  if (e != cudaSuccess) return e;
+                                  kern2<<<blocks, x.threads, smem, stream>>>(static_cast<T*>(A), ipiv, info, batch);
+                                  return cudaGetLastError();
+                              });
+        }
+    }
     static KernelCache cache[kMaxDevices];
     auto kern = lub_lapack_kernel<T, N, LUONLY>;
-    LaunchCtx x{batch, threads_req > 0 ? threads_req : 256, stream, li, (flags & kLaunchDryRun) != 0, ev0, dev};
     return run_kernel(kern, cache[dev], x, kMaxThreads, [](int w) { return L::smem_bytes(w); }, L::MPW, L::G,
                       LUONLY ? "lub_lapack_kernel<LUONLY>" : "lub_lapack_kernel", [&](unsigned blocks, int smem) {
                           cudaError_t e = ev0 ? cudaEventRecord(ev0, stream) : cudaSuccess;

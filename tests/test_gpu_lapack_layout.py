@@ -93,8 +93,12 @@ def test_lapack_info_reports_the_first_zero_pivot():
         X, ipiv, info = gpu_lapack(A)
         _, ipiv_ref, info_ref = O.lapack_getrf(A)
         assert info[3] == 1 and info[5] == 3
-        assert np.array_equal(info != 0, info_ref != 0)
-        first = np.where(info != 0)[0]
+        # matrix 7 (two equal rows) hangs on whether fl(p * fl(1 / p)) == 1 for the pivot p the equal rows meet at: a last
+        # pivot of exactly zero (info = n) and a tiny one (info = 0) are both what a getrf can return for it
+        keep = np.arange(40) != 7
+        assert np.array_equal((info != 0)[keep], (info_ref != 0)[keep])
+        assert info[7] in (0, n)
+        first = np.where((info != 0) & keep)[0]
         assert np.array_equal(info[first], info_ref[first])
         for b in range(40):
             k = info[b] if info[b] else n          # pivots are comparable up to and including the zero pivot's step
