@@ -145,8 +145,10 @@ int lu_batched_get_threads(int n, int dtype);
 /* Ablation knobs of the calling thread (the thesis keeps its variants as sibling directories --
  * swzl/luBatchedInplace.cuh:12-20 staging layout, shfl/luBatchedInplace.cuh:12-53 exchange, no_templ/ runtime N; here the
  * variants that exist as kernels in the library are selectable at run time; same pivots, values equal to rounding):
- *   LUB_OPT_STAGING      0 = library choice (TMA bulk tensor copies into a swizzled image where the row size allows),
- *                        1 = LSU staging (128-bit loads / cp.async into a padded or dense image) for every size;
+ *   LUB_OPT_STAGING      0 = library choice (TMA bulk tensor copies into a swizzled image where rows are 128 / 256 bytes or
+ *                            padded to a line, 1-D cp.async.bulk span copies into a dense image elsewhere from N = 5 on),
+ *                        1 = LSU staging (128-bit loads / cp.async into a padded or dense image) for every size, and the
+ *                            lane = row kernel for pivot_mode 3;
  *   LUB_OPT_FP64_TENSOR  fp64 N = 32, blocked elimination with DMMA rank-4 updates (csrc/lub_dmma.cuh):
  *                        0 = library choice: without pivoting only (as accurate as the unblocked elimination there);
  *                        1 = never (DFMA rank-1 updates with shuffle exchange);
