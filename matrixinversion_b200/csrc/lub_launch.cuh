@@ -184,6 +184,9 @@ struct BulkChoice { bool on; int gr, gc, minb, maxt, threads, opt; };
 #ifndef LUB_BULK_F64_EXC
 #define LUB_BULK_F64_EXC 1
 #endif
+#ifndef LUB_BULK_SMALL4
+#define LUB_BULK_SMALL4 1
+#endif
 #ifndef LUB_BULK_PAR4
 #define LUB_BULK_PAR4 1
 #endif
@@ -194,9 +197,11 @@ constexpr BulkChoice pick_bulk(int n, int es, int mode) {
     // (fp64 exceptions, measured slower: profiles/r02_bulk_ab_f64_*.json)
     const bool f64_off = n == 16 || n == 32 || (LUB_BULK_F64_EXC && (n == 8 || (mode == kModeNone && (n == 13 || n == 18 || n == 20)) ||
                          (mode == kModeSerial && n == 20)));
-    // fp32 parallel pivoting at N = 12, 20, 24, 28: the position-aware row-wise search on the dense image
-    const bool f32_par4 = LUB_BULK_PAR4 && mode == kModeParallel && (n == 12 || n == 20 || n == 24 || n == 28);
-    const bool on = n >= LUB_BULK_MIN_N && ((es == 4) ? (n % 4 != 0 || f32_par4) : !f64_off);
+    // fp32 parallel pivoting at N = 20, 24, 28 (other modes: TMA): the position-aware row-wise search on the dense image
+    const bool f32_par4 = LUB_BULK_PAR4 && mode == kModeParallel && (n == 20 || n == 24 || n == 28);
+    // fp32 N = 12, 16 in every mode (N = 12 serial: 0.43 -> 0.27 ms, N = 16: -3..-5 %; N = 8 loses: 0.10 -> 0.14 without pivoting)
+    const bool f32_small4 = LUB_BULK_SMALL4 && (n == 12 || n == 16);
+    const bool on = n >= LUB_BULK_MIN_N && ((es == 4) ? (n % 4 != 0 || f32_par4 || f32_small4) : !f64_off);
     if (!on) return BulkChoice{false, c.gr, c.gc, 1, kMaxThreads, 256, 0};
     const int mpw = 32 / (c.gr * c.gc);
     const int img = (mpw * n * n * es + 15) / 16 * 16 + 16;

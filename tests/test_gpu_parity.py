@@ -264,11 +264,11 @@ def test_bulk_copy_paths_ragged_batches_and_lsu_staging_agree():
     the LSU-staged kernels (LUB_OPT_STAGING = 1) bit for bit."""
     guard = 5
     cases = ((5, np.float32), (7, np.float32), (13, np.float32), (18, np.float32), (22, np.float32), (27, np.float32), (31, np.float32),
-             (12, np.float32), (28, np.float32), (7, np.float64), (19, np.float64), (26, np.float64), (31, np.float64))
+             (12, np.float32), (16, np.float32), (28, np.float32), (7, np.float64), (19, np.float64), (26, np.float64), (31, np.float64))
     for n, dtype in cases:
         for mode in MODES:
-            if n % 4 == 0 and dtype == np.float32 and mode != 2:
-                continue  # fp32 multiples of 4 take this path with parallel pivoting only
+            if n in (20, 24, 28) and dtype == np.float32 and mode != 2:
+                continue  # fp32 N = 20, 24, 28 take this path with parallel pivoting only (TMA otherwise)
             assert lub.kernel_name(n, mode, dtype) == "lub_bulk_kernel", (n, dtype, mode)
             A = synthetic(n, 203 + guard, dtype, dominant=(mode == 0))
             Xfull, pfull = gpu_invert(A, mode)
@@ -507,6 +507,16 @@ def test_config5_n32_1M_fp64_pivot_nondominant_pivots():
 
 def test_serial_n31_1M_fp32_nondominant_pivots():
     _nondominant_full_size(31, 1_000_000, np.float32, 1)
+
+
+def test_parallel_n31_1M_fp32_nondominant_pivots():
+    """the position-aware row-wise search (csrc/lub_bulk.cuh) at full size: 16 of the 30 tree slots count at N = 31"""
+    _nondominant_full_size(31, 1_000_000, np.float32, 2)
+
+
+def test_parallel_n27_1M_fp64_nondominant_pivots():
+    """fp64 on the bulk-copy staged kernel: odd tile spans, upper-word pivot search with the exact 64-bit fallback"""
+    _nondominant_full_size(27, 1_000_000, np.float64, 2)
 
 
 def test_raw_six_argument_entry_point_on_a_caller_stream():
