@@ -252,12 +252,16 @@ lub_bulk_kernel(T* __restrict__ A, int32_t* __restrict__ piv, long long batch) {
 
     const long long ntiles = (batch + MPW - 1) / MPW;
     const long long tstride = (long long)gridDim.x * nwarps;
-    const unsigned char* Ab = reinterpret_cast<const unsigned char*>(A);
-    const long long batch_bytes = batch * (long long)(MS * ES);
+    // Byte offsets are taken from the 16-byte boundary at or below A: layouts with scalar rows (CH == 1, odd N) then serve any
+    // element-aligned batch pointer -- a view that starts at an odd matrix index is 4, 8 or 12 bytes off -- through the same
+    // head / tail handling; the layouts with vector rows need (and the launcher guarantees) a0 == 0.
+    const long long a0 = (CH == 1) ? (long long)(reinterpret_cast<uintptr_t>(A) & 15) : 0;
+    const unsigned char* Ab = reinterpret_cast<const unsigned char*>(A) - a0;
+    const long long batch_bytes = a0 + batch * (long long)(MS * ES);
 
     // lane 0: request the span of `tile` into image buffer `buf`, completion on `bar` (+ its own cp.async group)
     auto request = [&](long long tile, unsigned char* buf, unsigned long long* bar) {
-        const long long s = tile * (long long)L::SPAN_BYTES;
+        const long long s = a0 + tile * (long long)L::SPAN_BYTES;
         long long e = s + L::SPAN_BYTES;
         if (e > batch_bytes) e = batch_bytes;
         const long long s16 = s & ~15ll, e16 = e & ~15ll;
@@ -280,9 +284,9 @@ lub_bulk_kernel(T* __restrict__ A, int32_t* __restrict__ piv, long long batch) {
         if (tile >= ntiles) continue;
         const long long first = tile * MPW;
         const int nm = (batch - first < MPW) ? (int)(batch - first) : MPW;
-        const long long s = tile * (long long)L::SPAN_BYTES;
+        const long long s = a0 + tile * (long long)L::SPAN_BYTES;
         const long long e = s + (long long)nm * (MS * ES);
-        const unsigned mis = L::ALIGNED ? 0u : (unsigned)(s & 15);
+        const unsigned mis = (L::ALIGNED && CH != 1) ? 0u : (unsigned)(s & 15);
 
         const unsigned cur = (NIMG == 2) ? (iter & 1u) : 0u;
         unsigned char* buf = wbase + cur * L::IMG_BYTES;
@@ -393,13 +397,13 @@ lub_bulk_kernel(T* __restrict__ A, int32_t* __restrict__ piv, long long batch) {
         {
             // aligned interior by one bulk store; up to three words at either end by plain stores
             const long long s16u = (s + 15) & ~15ll, e16 = e & ~15ll;
-            unsigned char* gdst = reinterpret_cast<unsigned char*>(A);
+            unsigned char* gdst = reinterpret_cast<unsigned char*>(A) - a0;
             if (lane == 0) {
                 if (e16 > s16u) bulk_store(gdst + s16u, buf + mis + (s16u - s), (unsigned)(e16 - s16u));
                 tma_store_commit();
             }
             const int hw = (int)(s16u - s) >> 2, tw = (int)(e - e16) >> 2;  // head / tail words (0..3)
-            if (!L::ALIGNED && lane < hw)
+            if ((!L::ALIGNED || CH == 1) && lane < hw)
                 *reinterpret_cast<unsigned*>(gdst + s + 4 * lane) = *reinterpret_cast<const unsigned*>(buf + mis + 4 * lane);
             if (lane >= 4 && lane < 4 + tw)
                 *reinterpret_cast<unsigned*>(gdst + e16 + 4 * (lane - 4)) = *reinterpret_cast<const unsigned*>(buf + mis + (e16 - s) + 4 * (lane - 4));

@@ -441,8 +441,9 @@ cudaError_t launch(void* A, int32_t* piv, long long batch, int threads_req, cuda
     // rows that are not 16-byte multiples: 1-D bulk copies instead of a tensor map (lub_bulk.cuh); any batch size
     using BC = BulkCfg<T, N, MODE>;
     if constexpr (BC::ON) {
-        if (fast && !no_tma) {
-            using BL = BulkLayout<T, N, BC::GR, BC::GC, MODE>;
+        using BL = BulkLayout<T, N, BC::GR, BC::GC, MODE>;
+        // scalar-row layouts (odd N) take any element-aligned pointer: a view starting at an odd matrix index stays on this path
+        if ((fast || (BL::CH == 1 && reinterpret_cast<uintptr_t>(A) % sizeof(T) == 0)) && !no_tma) {
             auto kern = lub_bulk_kernel<T, N, BC::GR, BC::GC, MODE, BC::MINB, false, BC::OPT, BC::MAXT>;
             if (threads_req <= 0) x.threads = BC::THREADS;
             return run_kernel(kern, cache_fast[dev], x, BC::MAXT, [](int w) { return BL::smem_bytes(w, 2); }, BL::MPW, BL::G, "lub_bulk_kernel",

@@ -211,17 +211,20 @@ def test_edge_cases():
     # batch = 1, piv = None, N = 1
     X, _ = gpu_invert(np.full((1, 1, 1), 4.0, np.float32), 2, want_piv=False)
     assert X[0, 0, 0] == pytest.approx(0.25)
-    # pointer aligned to the element but not to 16 bytes (odd N, view starting at matrix 1)
-    for n, dtype in ((5, np.float32), (31, np.float32), (7, np.float64), (19, np.float32)):
-        A = synthetic(n, 41, dtype)
-        base = torch.from_numpy(A).cuda()
-        view = base[1:]
-        assert view.data_ptr() % 16 != 0 or n * n * A.itemsize % 16 == 0
-        piv = torch.zeros((40, n), dtype=torch.int32, device="cuda")
-        lub.lu_batched_inplace(view, piv, "parallel")
-        Xfull, pfull = gpu_invert(A[1:], 2)
-        assert np.array_equal(view.cpu().numpy(), Xfull) and np.array_equal(piv.cpu().numpy(), pfull)
-        assert np.array_equal(base[0].cpu().numpy(), A[0])  # neighbour untouched
+    # pointer aligned to the element but not to 16 bytes (odd N, views starting at matrix 1, 2, 3): the bulk-copy staged
+    # kernel serves them through its head / tail words, bit for bit like the aligned launch; neighbours on both sides stay
+    for n, dtype in ((5, np.float32), (31, np.float32), (7, np.float64), (19, np.float32), (27, np.float64)):
+        A = synthetic(n, 44, dtype)
+        for first in (1, 2, 3):
+            base = torch.from_numpy(A).cuda()
+            view = base[first:43]
+            assert first != 1 or view.data_ptr() % 16 != 0
+            piv = torch.zeros((43 - first, n), dtype=torch.int32, device="cuda")
+            lub.lu_batched_inplace(view, piv, "parallel")
+            Xfull, pfull = gpu_invert(A[first:43], 2)
+            assert np.array_equal(view.cpu().numpy(), Xfull) and np.array_equal(piv.cpu().numpy(), pfull), (n, dtype, first)
+            got = base.cpu().numpy()
+            assert np.array_equal(got[:first], A[:first]) and np.array_equal(got[43], A[43])  # neighbours untouched
     # singular input: inf/NaN, no status, no crash (Q7)
     X, piv = gpu_invert(np.zeros((3, 6, 6), np.float32), 1)
     assert not np.isfinite(X).any() and np.array_equal(piv, np.tile(np.arange(6, dtype=np.int32), (3, 1)))
