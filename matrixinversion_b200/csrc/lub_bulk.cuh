@@ -26,6 +26,7 @@
 // row's current position as a one-hot word.
 #pragma once
 #include "lub_tma.cuh"
+#include "lub_lapack.cuh"
 
 namespace lub {
 
@@ -54,7 +55,9 @@ struct BulkLayout {
     static constexpr int SPAN_BYTES = MPW * MS * ES;
     static constexpr bool ALIGNED = (SPAN_BYTES % 16) == 0;  // every full tile starts on 16 bytes
     static constexpr int IMG_BYTES = roundup_(SPAN_BYTES, 16) + 16;
-    static constexpr int PERM_BYTES = (MODE != kModeNone) ? roundup_(MPW * N * 4, 16) : 0;
+    // pivot_mode 3 keeps two vectors per matrix: the permutation the load applies, and LAPACK's ipiv for the caller
+    static constexpr int PERM1_BYTES = (MODE != kModeNone) ? roundup_(MPW * N * 4, 16) : 0;
+    static constexpr int PERM_BYTES = (MODE == kModeLapack) ? 2 * PERM1_BYTES : PERM1_BYTES;
     static constexpr int HEADER_BYTES = 64;
     static constexpr int warp_bytes(int nimg) { return nimg * IMG_BYTES + PERM_BYTES + 16; }
     static constexpr int smem_bytes(int warps, int nimg) { return HEADER_BYTES + warps * warp_bytes(nimg); }
@@ -215,14 +218,17 @@ __device__ __forceinline__ void prepass_rowpos(const T* __restrict__ img0, int* 
 constexpr int kBulkLean = 1;      // gj_eliminate_lean
 constexpr int kBulkOldSearch = 2; // the position-wise search of lub_fast.cuh (for comparison)
 constexpr int kBulkSingle = 4;    // one image per warp (no prefetch)
+constexpr int kBulkLuOnly = 64;   // pivot_mode 3 only: stop after the LU factorisation of prepass_getrf and store the factors
 constexpr int kBulkGroupSearch = 16; // N <= 16: every lane group searches its own matrix (prepass_group) instead of warp-wide searches
 
 template <typename T, int N, int GR, int GC, int MODE, int MINB = 1, bool BSYNC = false, int OPT = kBulkLean, int MAXT = kMaxThreads>
 __global__ void __launch_bounds__(MAXT, MINB)
-lub_bulk_kernel(T* __restrict__ A, int32_t* __restrict__ piv, long long batch) {
+lub_bulk_kernel(T* __restrict__ A, int32_t* __restrict__ piv, long long batch, int32_t* __restrict__ info = nullptr) {
     using L = BulkLayout<T, N, GR, GC, MODE>;
     constexpr bool LEAN = (OPT & kBulkLean) != 0, OLDS = (OPT & kBulkOldSearch) != 0;
     constexpr int NIMG = (OPT & kBulkSingle) ? 1 : 2;
+    constexpr bool LUONLY = (OPT & kBulkLuOnly) != 0;
+    static_assert(!LUONLY || MODE == kModeLapack, "the factors-only form belongs to pivot_mode 3");
     constexpr int G = L::G, MPW = L::MPW, LR = L::LR, LC = L::LC, CH = L::CH, CPL = L::CPL, CPR = L::CPR;
     constexpr int P = L::P, MS = L::MS, ES = L::ES;
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -234,6 +240,7 @@ lub_bulk_kernel(T* __restrict__ A, int32_t* __restrict__ piv, long long batch) {
     constexpr int WARP_BYTES = NIMG * L::IMG_BYTES + L::PERM_BYTES + 16;
     unsigned char* wbase = smem_raw + L::HEADER_BYTES + (size_t)warp * WARP_BYTES;
     int* perm_all = reinterpret_cast<int*>(wbase + NIMG * L::IMG_BYTES);
+    int* ipiv_all = perm_all + L::PERM1_BYTES / 4;  // MODE == kModeLapack only
     unsigned long long* bar0 = reinterpret_cast<unsigned long long*>(wbase + NIMG * L::IMG_BYTES + L::PERM_BYTES);
 
     if (MODE == kModeParallel && threadIdx.x < N) slot_rank[threadIdx.x] = (int8_t)tree_slot_rank(threadIdx.x, N);
@@ -304,7 +311,15 @@ lub_bulk_kernel(T* __restrict__ A, int32_t* __restrict__ piv, long long batch) {
         T* img = reinterpret_cast<T*>(buf + mis);
         T* mimg = img + ml * MS;
         int* perm = perm_all + ml * N;
-        if (MODE != kModeNone && N <= 16 && (OPT & kBulkGroupSearch) != 0) {
+        if constexpr (MODE == kModeLapack) {
+            // true partial pivoting: the permutation comes out of an LU factorisation of the staged matrix (prepass_getrf)
+#pragma unroll 1
+            for (int m = 0; m < MPW; ++m) {
+                const int fz = prepass_getrf<T, N, P, LUONLY>(img + m * MS, perm_all + m * N, ipiv_all + m * N, lane);
+                if (lane == 0 && m < nm && info != nullptr) info[first + m] = fz;
+            }
+            __syncwarp();
+        } else if (MODE != kModeNone && N <= 16 && (OPT & kBulkGroupSearch) != 0) {
             prepass_group<T, N, G, MODE, P>(mimg, perm, slot_rank, g);
             __syncwarp();
         } else if (MODE != kModeNone) {
@@ -321,6 +336,15 @@ lub_bulk_kernel(T* __restrict__ A, int32_t* __restrict__ piv, long long batch) {
             __syncwarp();
         }
 
+        if constexpr (LUONLY && NIMG == 2) {  // factors only: the image already holds the result; fetch the next tile
+            __syncwarp();
+            const long long nxt = tile + tstride;
+            if (lane == 0 && nxt < ntiles) {
+                tma_store_wait_read();
+                request(nxt, wbase + (cur ^ 1u) * L::IMG_BYTES, bar0 + (cur ^ 1u));
+            }
+        }
+        if constexpr (!LUONLY) {
         // ---- registers <- image: rows permuted, LR x LC block per lane ---------------------
         T a[LR][LC];
 #pragma unroll
@@ -392,6 +416,7 @@ lub_bulk_kernel(T* __restrict__ A, int32_t* __restrict__ piv, long long batch) {
                     if (rok && ((GC * LC <= N) || (pcol[lj] >= 0))) mimg[i * P + pcol[lj]] = a[li][lj];
             }
         }
+        }  // !LUONLY
         fence_proxy_async();  // generic-proxy writes -> visible to the bulk-copy unit
         __syncwarp();
         {
@@ -413,7 +438,7 @@ lub_bulk_kernel(T* __restrict__ A, int32_t* __restrict__ piv, long long batch) {
         if (pivp != nullptr) {
             int32_t* pdst = pivp + first * N;
             for (int x = lane; x < nm * N; x += 32)
-                pdst[x] = (MODE != kModeNone) ? perm_all[x] : (x % N);
+                pdst[x] = (MODE == kModeLapack) ? ipiv_all[x] : ((MODE != kModeNone) ? perm_all[x] : (x % N));
         }
         __syncwarp();
     }

@@ -31,6 +31,7 @@
 namespace lub {
 
 constexpr int kModeNone = 0, kModeSerial = 1, kModeParallel = 2;
+constexpr int kModeLapack = 3;  // true partial pivoting (getrf): lub_lapack*.cuh, lub_bulk.cuh, lub_interleaved.cuh
 constexpr int kMaxThreads = 256;  // upper bound of the NUMTHREADS knob (keeps 255 registers available)
 
 // ---- small helpers ---------------------------------------------------------------------

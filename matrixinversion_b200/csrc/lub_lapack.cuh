@@ -28,11 +28,10 @@
 //   info[b]    = 0, or k + 1 for the first exactly-zero pivot U(k,k) (then the inverse of that matrix is not
 //                meaningful: inf / NaN, as LAPACK's getri refuses it).
 #pragma once
-#include "lub_kernel.cuh"
+#include "lub_fast.cuh"
 
 namespace lub {
 
-constexpr int kModeLapack = 3;
 
 constexpr int pow2_ceil(int n) { int g = 1; while (g < n) g *= 2; return g; }
 
@@ -43,6 +42,122 @@ __device__ __forceinline__ unsigned long long group_max_bits(unsigned mask, unsi
     const uint32_t mh = __reduce_max_sync(mask, hi);
     const uint32_t ml = __reduce_max_sync(mask, hi == mh ? lo : 0u);
     return ((unsigned long long)mh << 32) | ml;
+}
+
+// Round 2, two-phase form of pivot_mode 3 (used by lub_bulk_kernel<..., MODE = kModeLapack>): the permutation of getrf
+// is a function of the UPDATED columns, so it is found by running the LU factorisation itself (n^3 / 3 FMAs, a third
+// of the inversion) in the lane = row layout on a staged image -- the pivot row is a run-time lane, its trailing
+// part travels by N - 1 - k shuffles -- and then the inverse is computed by the same permuted-load / register
+// Gauss-Jordan / column-scatter machinery as modes 1 / 2, whose diagonal pivots under that permutation ARE getrf's.
+// N (N - 1) / 2 shuffles for the search phase instead of N^2 for a lane = row Gauss-Jordan.
+//   mimg: the matrix (row stride P) in shared memory; perm[i] <- original row that getrf moves to position i;
+//   ipiv_s[k] <- LAPACK's 1-based swap position of step k; returns info (0, or k + 1 for the first exactly-zero pivot).
+// The arithmetic is the getf2 recurrence of lub_lapack_kernel<LUONLY> (reciprocal scaling, fma(-l, r, a)), so both
+// mode-3 kernels pick the same pivots.  Every lane of the warp must call this; lanes >= N idle along.
+// isamax of one step: the first maximum (lowest position) of |col| over the rows at positions >= k
+template <typename T>
+__device__ __forceinline__ void getrf_search(T col, int pos, bool mine, int k, int lane, int& p, int& pl, bool& zero) {
+    using U = typename FpBits<T>::U;
+    const bool cand = mine && (pos >= k);
+    const U key = cand ? FpBits<T>::absbits(col) : U(0);
+    const U mx = group_max_bits(0xffffffffu, key);
+    const unsigned sel = (cand && key == mx) ? (((unsigned)pos << 8) | (unsigned)lane) : 0xffffu;
+    const unsigned win = __reduce_min_sync(0xffffffffu, sel);
+    p = (int)(win >> 8);
+    pl = (int)(win & 0xffu);
+    zero = (mx == U(0));
+}
+
+// LU = true: the factors themselves are the result (lu_batched_factor_inplace, pivot_mode 3): the multipliers are kept in
+// column k and every lane writes its row back into the image at the row's final position -- P A = L U, rows in swapped
+// order, as lub_lapack_kernel<LUONLY> leaves them.
+// getrf_core works on the row every lane has loaded (a[], lane = original row) and leaves the row's final position in pos;
+// the wrappers below load / store the rows from a dense image (here) or a 128-byte-swizzled one (lub_tma.cuh).
+template <typename T, int N, bool LU>
+__device__ __forceinline__ int getrf_core(T (&a)[N], int& pos, int* __restrict__ perm, int* __restrict__ ipiv_s, int lane) {
+    const bool mine = lane < N;
+    pos = lane;          // position of this lane's row in LAPACK's row order (rows never move)
+    int first_zero = 0;  // info
+    int p, pl;
+    bool zero;
+    if constexpr (sizeof(T) == 4) {
+        // Software pipeline (fp32): a step's critical path is search (two warp reductions) -> broadcast of the pivot row ->
+        // update, and one warp runs one matrix, so the order of the code is the order of execution.  Column k + 1 is
+        // therefore updated FIRST, the search of step k + 1 is issued right behind it and the rest of the pivot row travels
+        // while those reductions are in flight; every lane also takes the reciprocal of its own candidate ahead of time,
+        // so the pivot's comes with one shuffle instead of a division on the critical path (N = 32: 7.19 -> 6.78 ms).
+        T rown = T(1) / a[0];
+        getrf_search<T>(a[0], pos, mine, 0, lane, p, pl, zero);
+#pragma unroll
+        for (int k = 0; k < N; ++k) {
+            if (zero && first_zero == 0) first_zero = k + 1;
+            if (pos == k) pos = p;
+            if (lane == pl) pos = k;
+            if (lane == 0) ipiv_s[k] = p + 1;
+            if (k < N - 1) {
+                const int plk = pl;
+                const T rinv = __shfl_sync(0xffffffffu, rown, plk);
+                const bool below = mine && pos > k;
+                const T l = below ? a[k] * rinv : T(0);
+                if (LU && below) a[k] = l;
+                {
+                    const T r = __shfl_sync(0xffffffffu, a[k + 1], plk);
+                    a[k + 1] = fma(-l, r, a[k + 1]);
+                }
+                rown = T(1) / a[k + 1];
+                getrf_search<T>(a[k + 1], pos, mine, k + 1, lane, p, pl, zero);
+#pragma unroll
+                for (int j = k + 2; j < N; ++j) {
+                    const T r = __shfl_sync(0xffffffffu, a[j], plk);
+                    a[j] = fma(-l, r, a[j]);
+                }
+            }
+        }
+    } else {
+        // fp64: the plain order -- the pipelined form holds more doubles live than 168 registers take (N = 27: 9.1 vs 10.2 ms)
+#pragma unroll
+        for (int k = 0; k < N; ++k) {
+            getrf_search<T>(a[k], pos, mine, k, lane, p, pl, zero);
+            if (zero && first_zero == 0) first_zero = k + 1;
+            if (pos == k) pos = p;
+            if (lane == pl) pos = k;
+            if (lane == 0) ipiv_s[k] = p + 1;
+            if (k < N - 1) {
+                const T pv = __shfl_sync(0xffffffffu, a[k], pl);
+                const T rinv = T(1) / pv;
+                const bool below = mine && pos > k;
+                const T l = below ? a[k] * rinv : T(0);
+                if (LU && below) a[k] = l;
+#pragma unroll
+                for (int j = k + 1; j < N; ++j) {
+                    const T r = __shfl_sync(0xffffffffu, a[j], pl);
+                    a[j] = fma(-l, r, a[j]);
+                }
+            }
+        }
+    }
+    if (mine) perm[pos] = lane;
+    return first_zero;
+}
+
+template <typename T, int N, int P, bool LU>
+__device__ __forceinline__ int prepass_getrf(T* __restrict__ mimg, int* __restrict__ perm, int* __restrict__ ipiv_s, int lane) {
+    const bool mine = lane < N;
+    const T* rowp = mimg + (mine ? lane : 0) * P;
+    T a[N];
+#pragma unroll
+    for (int j = 0; j < N; ++j) a[j] = rowp[j];
+    int pos;
+    const int first_zero = getrf_core<T, N, LU>(a, pos, perm, ipiv_s, lane);
+    if constexpr (LU) {
+        __syncwarp();  // every lane has long read its row; now the rows change places
+        if (mine) {
+            T* dst = mimg + pos * P;
+#pragma unroll
+            for (int j = 0; j < N; ++j) dst[j] = a[j];
+        }
+    }
+    return first_zero;
 }
 
 template <typename T, int N>

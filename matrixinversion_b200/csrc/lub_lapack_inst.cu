@@ -6,6 +6,11 @@
 
 namespace lub {
 
+#ifndef LUB_LAPACK_TWO_PHASE_MIN_N
+#define LUB_LAPACK_TWO_PHASE_MIN_N 9
+#endif
+constexpr int kLapackTwoPhaseMinN = LUB_LAPACK_TWO_PHASE_MIN_N;
+
 template <typename T, int N, bool LUONLY>
 static cudaError_t launch_lapack_n(void* A, int32_t* ipiv, int32_t* info, long long batch, int threads_req, cudaStream_t stream,
                                    LaunchInfo* li, int flags, cudaEvent_t ev0) {
@@ -15,6 +20,51 @@ static cudaError_t launch_lapack_n(void* A, int32_t* ipiv, int32_t* info, long l
     if (err != cudaSuccess) return err;
     if (dev < 0 || dev >= kMaxDevices) return cudaErrorInvalidDevice;
     LaunchCtx x{batch, threads_req > 0 ? threads_req : 256, stream, li, (flags & kLaunchDryRun) != 0, ev0, dev};
+    // N >= kLapackTwoPhaseMinN: the two-phase kernel -- getrf's permutation from an LU factorisation in the lane = row layout
+    // (prepass_getrf, N (N - 1) / 2 shuffles), then the permuted-load register Gauss-Jordan of modes 1 / 2
+    // (lub_bulk_kernel<..., kModeLapack>); LU only: the first phase alone, factors stored from its registers.
+    // LUB_OPT_STAGING = 1 keeps the one-phase kernels below.  Measured: profiles/r02_mode3_twophase.md.
+    // ... on the swizzled TMA image where the rows are whole 128-byte lines (fp32 N = 32, fp64 N = 16, 32): the lane = row
+    // accesses of the first phase are 8-way bank conflicts on a dense image whose rows are a multiple of 32 banks
+    if constexpr (N >= kLapackTwoPhaseMinN && (N * sizeof(T)) % 128 == 0 && TmaCfg<T, N, kModeParallel>::ON) {
+        using TC = TmaCfg<T, N, kModeParallel>;
+        using VC = V3Cfg<T, N, kModeParallel>;
+        using TL = TmaLayout<T, N, TC::GR, TC::GC, kModeLapack>;
+        if ((x.dry_run || reinterpret_cast<uintptr_t>(A) % 16 == 0) && batch <= 0x7fffff00ll && !(flags & kLaunchNoTma)) {
+            constexpr int NIMG = (TC::OPT & kTmaDB) ? 2 : 1;
+            static KernelCache cache4[kMaxDevices];
+            auto kern4 = lub_tma_kernel<T, N, TC::GR, TC::GC, kModeLapack, (TC::MAXT > kMaxThreads ? 1 : VC::MINB), TC::BSYNC, false, false, false,
+                                        TC::OPT | (LUONLY ? kTmaLuOnly : 0), TC::MAXT>;
+            if (threads_req <= 0) x.threads = TC::THREADS;
+            return run_kernel(kern4, cache4[dev], x, TC::MAXT, [](int w) { return TL::smem_bytes(w, NIMG); }, TL::MPW, TL::G,
+                              LUONLY ? "lub_tma_kernel<getrf, LUONLY>" : "lub_tma_kernel<getrf>", [&](unsigned blocks, int smem) {
+                                  const CUtensorMap* map = nullptr;
+                                  cudaError_t e = cached_batch_tmap<T>(&map, A, N, batch, TL::MPW, dev);
+                                  if (e != cudaSuccess) return e;
+                                  e = ev0 ? cudaEventRecord(ev0, stream) : cudaSuccess;
+                                  if (e != cudaSuccess) return e;
+                                  kern4<<<blocks, x.threads, smem, stream>>>(*map, static_cast<T*>(A), ipiv, batch, info);
+                                  return cudaGetLastError();
+                              });
+        }
+    }
+    if constexpr (N >= kLapackTwoPhaseMinN) {
+        using BC = BulkCfg<T, N, kModeLapack>;
+        using BL = BulkLayout<T, N, BC::GR, BC::GC, kModeLapack>;
+        const bool ok = x.dry_run || reinterpret_cast<uintptr_t>(A) % 16 == 0 || (BL::CH == 1 && reinterpret_cast<uintptr_t>(A) % sizeof(T) == 0);
+        if (ok && !(flags & kLaunchNoTma)) {
+            static KernelCache cache3[kMaxDevices];
+            auto kern3 = lub_bulk_kernel<T, N, BC::GR, BC::GC, kModeLapack, BC::MINB, false, BC::OPT | (LUONLY ? kBulkLuOnly : 0), BC::MAXT>;
+            if (threads_req <= 0) x.threads = BC::THREADS;
+            return run_kernel(kern3, cache3[dev], x, BC::MAXT, [](int w) { return BL::smem_bytes(w, 2); }, BL::MPW, BL::G,
+                              LUONLY ? "lub_bulk_kernel<getrf, LUONLY>" : "lub_bulk_kernel<getrf>", [&](unsigned blocks, int smem) {
+                                  cudaError_t e = ev0 ? cudaEventRecord(ev0, stream) : cudaSuccess;
+                                  if (e != cudaSuccess) return e;
+                                  kern3<<<blocks, x.threads, smem, stream>>>(static_cast<T*>(A), ipiv, batch, info);
+                                  return cudaGetLastError();
+                              });
+        }
+    }
     // N >= 17: the 2-D lane grid with bulk-copy staging (lub_lapack2.cuh) -- 13 instead of N shuffles per step; needs a
     // 16-byte aligned batch like every bulk / TMA path.  LUB_OPT_STAGING = 1 keeps the lane = row kernel.
     // (measured, profiles/r02_mode3_grid.jsonl: fp64 1.1-1.6x faster from N = 17 on -- N = 32: 31.7 -> 21.2 ms; fp32 only at N = 32,

@@ -190,7 +190,9 @@ struct BulkChoice { bool on; int gr, gc, minb, maxt, threads, opt; };
 #ifndef LUB_BULK_PAR4
 #define LUB_BULK_PAR4 1
 #endif
-constexpr BulkChoice pick_bulk(int n, int es, int mode) {
+// `lapack`: the two-phase pivot_mode 3 kernel (MODE = kModeLapack; call with mode = kModeParallel for the block shape): every
+// N, two pivot vectors per matrix in shared memory.
+constexpr BulkChoice pick_bulk(int n, int es, int mode, bool lapack = false) {
     const Cfg c = pick_bulk_cfg(n, es, mode);
     // fp32: the sizes without 16-byte rows; fp64: every size but the two TMA / DMMA ones (N = 16, 32) -- there the
     // bulk-staged block layout also beats the rolled-step kernel of lub_v4.cuh (N = 31: 7.7 -> 5.8 ms without pivoting)
@@ -201,11 +203,11 @@ constexpr BulkChoice pick_bulk(int n, int es, int mode) {
     const bool f32_par4 = LUB_BULK_PAR4 && mode == kModeParallel && (n == 20 || n == 24 || n == 28);
     // fp32 N = 12, 16 in every mode (N = 12 serial: 0.43 -> 0.27 ms, N = 16: -3..-5 %; N = 8 loses: 0.10 -> 0.14 without pivoting)
     const bool f32_small4 = LUB_BULK_SMALL4 && (n == 12 || n == 16);
-    const bool on = n >= LUB_BULK_MIN_N && ((es == 4) ? (n % 4 != 0 || f32_par4 || f32_small4) : !f64_off);
+    const bool on = lapack || (n >= LUB_BULK_MIN_N && ((es == 4) ? (n % 4 != 0 || f32_par4 || f32_small4) : !f64_off));
     if (!on) return BulkChoice{false, c.gr, c.gc, 1, kMaxThreads, 256, 0};
     const int mpw = 32 / (c.gr * c.gc);
     const int img = (mpw * n * n * es + 15) / 16 * 16 + 16;
-    const int perm = (mode != kModeNone) ? (mpw * n * 4 + 15) / 16 * 16 : 0;
+    const int perm = ((mode != kModeNone) ? (mpw * n * 4 + 15) / 16 * 16 : 0) * (lapack ? 2 : 1);
     const int wb = 2 * img + perm + 16;
     int minb = pick_minb(n, es, mode != kModeNone);
     while (minb > 1 && minb * (64 + 8 * wb + 1024) > 233472) --minb;
@@ -222,7 +224,7 @@ constexpr BulkChoice pick_bulk(int n, int es, int mode) {
 }
 template <typename T, int N, int MODE>
 struct BulkCfg {
-    static constexpr BulkChoice c = pick_bulk(N, (int)sizeof(T), MODE);
+    static constexpr BulkChoice c = (MODE == kModeLapack) ? pick_bulk(N, (int)sizeof(T), kModeParallel, true) : pick_bulk(N, (int)sizeof(T), MODE);
     static constexpr bool ON = kUseTma && c.on;
     static constexpr int GR = c.gr, GC = c.gc, MINB = c.minb, MAXT = c.maxt, THREADS = c.threads, OPT = c.opt;
 };
@@ -433,7 +435,7 @@ cudaError_t launch(void* A, int32_t* piv, long long batch, int threads_req, cuda
                                   if (e != cudaSuccess) return e;
                                   e = start();
                                   if (e != cudaSuccess) return e;
-                                  kern<<<blocks, x.threads, smem, stream>>>(*map, At, piv, batch);
+                                  kern<<<blocks, x.threads, smem, stream>>>(*map, At, piv, batch, nullptr);
                                   return cudaGetLastError();
                               });
         }
@@ -450,7 +452,7 @@ cudaError_t launch(void* A, int32_t* piv, long long batch, int threads_req, cuda
                               [&](unsigned blocks, int smem) {
                                   cudaError_t e = start();
                                   if (e != cudaSuccess) return e;
-                                  kern<<<blocks, x.threads, smem, stream>>>(At, piv, batch);
+                                  kern<<<blocks, x.threads, smem, stream>>>(At, piv, batch, nullptr);
                                   return cudaGetLastError();
                               });
         }

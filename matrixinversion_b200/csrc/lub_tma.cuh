@@ -16,6 +16,7 @@
 #pragma once
 #include <cuda.h>
 #include "lub_v3.cuh"
+#include "lub_lapack.cuh"
 
 namespace lub {
 
@@ -93,7 +94,9 @@ struct TmaLayout {
     static constexpr int MAT_BYTES = N * RB;
     static constexpr int IMG_BYTES = MPW * MAT_BYTES;
     static_assert(IMG_BYTES % 1024 == 0, "swizzle atoms are 1 KB");
-    static constexpr int PERM_BYTES = (MODE != kModeNone) ? MPW * N * 4 : 0;
+    // pivot_mode 3 keeps two vectors per matrix: the permutation the load applies, and LAPACK's ipiv for the caller
+    static constexpr int PERM1_BYTES = (MODE != kModeNone) ? MPW * N * 4 : 0;
+    static constexpr int PERM_BYTES = (MODE == kModeLapack) ? 2 * PERM1_BYTES : PERM1_BYTES;
     static constexpr int HEADER_BYTES = 64;  // slot ranks of the reference tree (exact tie-break path)
     static constexpr int smem_bytes(int warps, int nimg = 1) {  // + 1 KB slack to align the images by hand
         return 1024 + warps * (nimg * IMG_BYTES + PERM_BYTES) + warps * 16 + HEADER_BYTES;
@@ -304,6 +307,30 @@ __device__ __forceinline__ void prepass_poswise_swz(const unsigned char* img, in
     }
 }
 
+// pivot_mode 3 on the swizzled image: getrf's permutation from the LU factorisation of prepass_getrf (lub_lapack.cuh), lane =
+// original row.  The swizzle makes the lane = row accesses (16-byte chunk q of 32 different rows) conflict-free, which the dense
+// image of lub_bulk.cuh cannot be when the row is a multiple of 32 banks (N = 32: 5.1 vs 3.2 ms at N = 31 for the factors).
+template <typename T, int N, bool LU>
+__device__ __forceinline__ int prepass_getrf_swz(unsigned char* __restrict__ img, int row0, int* __restrict__ perm, int* __restrict__ ipiv_s, int lane) {
+    constexpr int ES = sizeof(T), EPV = 16 / ES, RB = (N * ES + 127) / 128 * 128;
+    static_assert(N % EPV == 0, "whole 16-byte chunks per row");
+    const bool mine = lane < N;
+    const int row = mine ? lane : 0;
+    T a[N];
+#pragma unroll
+    for (int q = 0; q < N / EPV; ++q) ld_vec<T, EPV>(reinterpret_cast<const T*>(img + swz_byte<RB>(row0 + row, q << 4)), &a[q * EPV]);
+    int pos;
+    const int first_zero = getrf_core<T, N, LU>(a, pos, perm, ipiv_s, lane);
+    if constexpr (LU) {
+        __syncwarp();  // every lane has long read its row; now the rows change places
+        if (mine) {
+#pragma unroll
+            for (int q = 0; q < N / EPV; ++q) st_vec<T, EPV>(reinterpret_cast<T*>(img + swz_byte<RB>(row0 + pos, q << 4)), &a[q * EPV]);
+        }
+    }
+    return first_zero;
+}
+
 // 32-byte global store (STG.256, sm_100): one full sector per lane and instruction
 __device__ __forceinline__ void st_global_256(float* p, const float* v) {
     asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]),
@@ -330,14 +357,17 @@ __device__ __forceinline__ void st_global_256(double* p, const double* v) {
 // to the very end, get the prefetch that PF gives the no-pivot path.  MAXT = threads the kernel is compiled
 // for: 16 KB per warp means 12 warps per SM (one 384-thread block, up to 168 registers per thread).
 constexpr int kTmaLean = 1, kTmaDB = 2, kTmaFused = 4;
+constexpr int kTmaLuOnly = 8;  // pivot_mode 3 only: stop after the LU factorisation of prepass_getrf and store the factors
 template <typename T, int N, int GR, int GC, int MODE, int MINB = 2, bool BSYNC = true, bool PF = false, bool OUTIMG = false,
           bool ST256 = false, int OPT = 0, int MAXT = kMaxThreads>
 __global__ void __launch_bounds__(MAXT, MINB)
-lub_tma_kernel(const __grid_constant__ CUtensorMap tmap, T* __restrict__ A, int32_t* __restrict__ piv, long long batch) {
+lub_tma_kernel(const __grid_constant__ CUtensorMap tmap, T* __restrict__ A, int32_t* __restrict__ piv, long long batch,
+               int32_t* __restrict__ info = nullptr) {
     static_assert(!PF || MODE == kModeNone, "in-place prefetch: the pivot modes need the image for the column scatter");
     static_assert(!OUTIMG || (MODE == kModeNone && !PF), "OUTIMG is the no-pivot output path without in-place prefetch");
     constexpr bool VIA_IMG = (MODE != kModeNone) || OUTIMG;  // results go through the image and a bulk store
-    constexpr bool LEAN = (OPT & kTmaLean) != 0, DB = (OPT & kTmaDB) != 0;
+    constexpr bool LEAN = (OPT & kTmaLean) != 0, DB = (OPT & kTmaDB) != 0, LUONLY = (OPT & kTmaLuOnly) != 0;
+    static_assert(!LUONLY || MODE == kModeLapack, "the factors-only form belongs to pivot_mode 3");
     static_assert(!DB || (VIA_IMG && !PF), "DB is the double-buffered form of the image-output path");
     constexpr int NIMG = DB ? 2 : 1;
     using L = TmaLayout<T, N, GR, GC, MODE>;
@@ -354,6 +384,7 @@ lub_tma_kernel(const __grid_constant__ CUtensorMap tmap, T* __restrict__ A, int3
     unsigned char* img = img0;
     unsigned char* after = base + (size_t)nwarps * (NIMG * L::IMG_BYTES);
     int* perm_all = reinterpret_cast<int*>(after + (size_t)warp * L::PERM_BYTES);
+    int* ipiv_all = perm_all + L::PERM1_BYTES / 4;  // MODE == kModeLapack only
     unsigned long long* bar0 = reinterpret_cast<unsigned long long*>(after + (size_t)nwarps * L::PERM_BYTES) + 2 * warp;
     unsigned long long* bar = bar0;
     int8_t* slot_rank = reinterpret_cast<int8_t*>(after + (size_t)nwarps * L::PERM_BYTES + (size_t)nwarps * 16);
@@ -409,7 +440,14 @@ lub_tma_kernel(const __grid_constant__ CUtensorMap tmap, T* __restrict__ A, int3
 
         const int trow0 = ml * N;  // first tile row of this lane's matrix
         int* perm = perm_all + ml * N;
-        if (MODE != kModeNone) {
+        if constexpr (MODE == kModeLapack) {
+#pragma unroll 1
+            for (int m = 0; m < MPW; ++m) {
+                const int fz = prepass_getrf_swz<T, N, LUONLY>(img, m * N, perm_all + m * N, ipiv_all + m * N, lane);
+                if (lane == 0 && m < nm && info != nullptr) info[first + m] = fz;
+            }
+            __syncwarp();
+        } else if (MODE != kModeNone) {
             constexpr int MI = (MPW < 2) ? MPW : 2;
 #pragma unroll 1
             for (int m = 0; m < MPW; m += MI) {
@@ -421,6 +459,22 @@ lub_tma_kernel(const __grid_constant__ CUtensorMap tmap, T* __restrict__ A, int3
             __syncwarp();
         }
 
+        if constexpr (LUONLY) {  // factors only: the image already holds the result; fetch the next tile and store this one
+            if (DB) {
+                const long long nxt = tile + tstride;
+                if (lane == 0 && nxt < ntiles) {
+                    tma_store_wait_read();
+                    mbar_expect_tx(bar0 + (iter & 1u), (unsigned)L::IMG_BYTES);
+                    tma_load_tile<L::LPR>(img0 + (iter & 1u) * L::IMG_BYTES, &tmap, bar0 + (iter & 1u), (int)(nxt * MPW));
+                }
+            }
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) {
+                tma_store_tile<L::LPR>(&tmap, img, (int)first);
+                tma_store_commit();
+            }
+        } else {
         // ---- registers <- image: rows permuted, LR x LC block per lane ---------------------
         T a[LR][LC];
 #pragma unroll
@@ -525,12 +579,13 @@ lub_tma_kernel(const __grid_constant__ CUtensorMap tmap, T* __restrict__ A, int3
                 tma_store_commit();
             }
         }
+        }  // !LUONLY
         int32_t* pivp = piv;
         asm volatile("" : "+l"(pivp));  // opaque: no second copy of the tile loop for piv == NULL
         if (pivp != nullptr) {
             int32_t* pdst = pivp + first * N;
             for (int e = lane; e < nm * N; e += 32)
-                pdst[e] = (MODE != kModeNone) ? perm_all[e] : (e % N);
+                pdst[e] = (MODE == kModeLapack) ? ipiv_all[e] : ((MODE != kModeNone) ? perm_all[e] : (e % N));
         }
         __syncwarp();
     }

@@ -82,7 +82,7 @@ struct VT {
     static void launch(void* A, int* piv, long long batch, unsigned blocks, int threads, int smem, cudaStream_t s) {
         CUtensorMap map;
         if (make_batch_tmap<T>(&map, A, N, batch, L::MPW) != cudaSuccess) { printf("tensor map failed\n"); return; }
-        kern()<<<blocks, threads, smem, s>>>(map, (T*)A, piv, batch);
+        kern()<<<blocks, threads, smem, s>>>(map, (T*)A, piv, batch, nullptr);
     }
     static int occ(int threads, int smem) {
         int o = 0;
@@ -164,7 +164,7 @@ struct VB {
     static constexpr auto kern() { return lub_bulk_kernel<T, N, GR, GC, MODE, MINB, (OPT & 8) != 0, (OPT & ~8), MAXT>; }
     static void set_attr(int smem) { cudaFuncSetAttribute(kern(), cudaFuncAttributeMaxDynamicSharedMemorySize, smem); }
     static void launch(void* A, int* piv, long long batch, unsigned blocks, int threads, int smem, cudaStream_t s) {
-        kern()<<<blocks, threads, smem, s>>>((T*)A, piv, batch);
+        kern()<<<blocks, threads, smem, s>>>((T*)A, piv, batch, nullptr);
     }
     static int occ(int threads, int smem) {
         int o = 0;

@@ -119,6 +119,70 @@ def test_lapack_info_reports_the_first_zero_pivot():
 
 
 @pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_two_phase_lapack_kernels_agree_with_the_one_phase_kernels(dtype):
+    """pivot_mode 3 from n = 9 on runs the two-phase kernels (prepass_getrf: LU factorisation in the lane = row layout for the
+    permutation, then the permuted-load Gauss-Jordan of modes 1 / 2; on the bulk-copy image, or the swizzled TMA image where rows
+    are whole 128-byte lines).  LUB_OPT_STAGING = 1 selects the one-phase kernels (lub_lapack.cuh / lub_lapack2.cuh): same getf2
+    recurrence, so ipiv and info must be identical -- ragged batches, singular matrices included -- the factors equal to
+    rounding of the reciprocal, and the inverses within the c = 8 residual bound of each other's matrix."""
+    eps = EPS[np.dtype(dtype)]
+    tdt = torch.float32 if dtype == np.float32 else torch.float64
+    for n in (9, 12, 16, 17, 20, 23, 27, 31, 32):
+        name = lub.kernel_name(n, "lapack", dtype)
+        lines = (n * np.dtype(dtype).itemsize) % 128 == 0
+        assert name == ("lub_tma_kernel<getrf>" if lines else "lub_bulk_kernel<getrf>"), (n, name)
+        for batch in (1003, 2):                     # ragged last tiles; fewer matrices than one warp tile holds
+            A = synthetic(n, batch, dtype)
+            A[1] = 0                                # info = 1
+            if batch > 5:
+                A[5][:, 3] = 0                      # a zero column
+            for lu_only in (False, True):
+                X, ipiv, info = gpu_lapack(A, lu_only=lu_only)
+                lub.set_option("staging", 1)
+                try:
+                    assert "getrf" not in lub.kernel_name(n, "lapack", dtype)
+                    X1, ipiv1, info1 = gpu_lapack(A, lu_only=lu_only)
+                finally:
+                    lub.set_option("staging", 0)
+                assert np.array_equal(info, info1), (n, batch, lu_only)
+                good = info == 0
+                assert good.sum() >= batch - 2
+                assert np.array_equal(ipiv[good], ipiv1[good]), (n, batch, lu_only)
+                scale = np.abs(X1[good]).max(axis=(1, 2), keepdims=True)
+                if lu_only:
+                    assert np.all(np.abs(X[good] - X1[good]) <= 16 * n * eps * scale), (n, batch)
+                else:
+                    A64 = A[good].astype(np.float64)
+                    kappa = np.linalg.cond(A64)
+                    res = np.linalg.norm(A64 @ X[good].astype(np.float64) - np.eye(n), axis=(1, 2))
+                    ok = kappa < 0.001 / eps
+                    assert np.all(res[ok] <= C_LAPACK * n * eps * kappa[ok]), (n, batch, float((res[ok] / (n * eps * kappa[ok])).max()))
+    # full size: 200,000 distinct matrices through the reference's own predicate, and a view that starts at an odd matrix index
+    n = 32
+    g = torch.Generator(device="cuda").manual_seed(5)
+    A0 = torch.rand((200_000, n, n), generator=g, device="cuda", dtype=tdt)
+    dA = A0.clone()
+    piv = torch.zeros((200_000, n), dtype=torch.int32, device="cuda")
+    info = torch.full((200_000,), -1, dtype=torch.int32, device="cuda")
+    lub.lu_batched_inplace(dA, piv, "lapack", info=info)
+    torch.cuda.synchronize()
+    assert int(info.abs().sum()) == 0
+    assert int(piv.min()) >= 1 and int(piv.max()) <= n and bool((piv >= torch.arange(1, n + 1, device="cuda", dtype=torch.int32)).all())
+    good, bad, _ = lub.verify_inv(A0, dA)
+    assert good + bad == 200_000 and bad <= (1000 if dtype == np.float32 else 0), bad      # reference rule on this input: ~8 % bad
+    n = 27                                         # odd n, scalar rows: a view 27 * 27 elements into the buffer is 4 / 8 bytes off 16
+    A = synthetic(n, 301, dtype)
+    buf = torch.zeros((302, n, n), device="cuda", dtype=tdt)
+    buf[1:].copy_(torch.from_numpy(A))
+    view = buf[1:]
+    pv = torch.zeros((301, n), dtype=torch.int32, device="cuda")
+    lub.lu_batched_inplace(view, pv, "lapack")
+    ref, pref, _ = gpu_lapack(A)
+    torch.cuda.synchronize()
+    assert np.array_equal(pv.cpu().numpy(), pref) and np.array_equal(view.cpu().numpy(), ref) and float(buf[0].abs().max()) == 0.0
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
 def test_interleaved_layout_is_bitwise_equal_to_matrix_major(dtype):
     tdt = torch.float32 if dtype == np.float32 else torch.float64
     for n in range(1, 9):
