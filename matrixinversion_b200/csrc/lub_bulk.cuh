@@ -219,6 +219,7 @@ constexpr int kBulkLean = 1;      // gj_eliminate_lean
 constexpr int kBulkOldSearch = 2; // the position-wise search of lub_fast.cuh (for comparison)
 constexpr int kBulkSingle = 4;    // one image per warp (no prefetch)
 constexpr int kBulkLuOnly = 64;   // pivot_mode 3 only: stop after the LU factorisation of prepass_getrf and store the factors
+constexpr int kBulkGetrfSingle = 128; // pivot_mode 3, fp32: one matrix at a time in the search phase (for comparison)
 constexpr int kBulkGroupSearch = 16; // N <= 16: every lane group searches its own matrix (prepass_group) instead of warp-wide searches
 
 template <typename T, int N, int GR, int GC, int MODE, int MINB = 1, bool BSYNC = false, int OPT = kBulkLean, int MAXT = kMaxThreads>
@@ -313,10 +314,25 @@ lub_bulk_kernel(T* __restrict__ A, int32_t* __restrict__ piv, long long batch, i
         int* perm = perm_all + ml * N;
         if constexpr (MODE == kModeLapack) {
             // true partial pivoting: the permutation comes out of an LU factorisation of the staged matrix (prepass_getrf)
+            if constexpr (sizeof(T) == 4 && MPW >= 2 && N <= 20 && (OPT & kBulkGetrfSingle) == 0) {
+                // fp32, N <= 20: two matrices of the tile at a time, their steps interleaved (getrf_core_x2): -5..-10 %; from
+                // N = 24 on the phase is bound by throughput, not by its dependent chain, and the doubled code costs 3 %
+                // (profiles/r02_mode3_twophase.md)
 #pragma unroll 1
-            for (int m = 0; m < MPW; ++m) {
-                const int fz = prepass_getrf<T, N, P, LUONLY>(img + m * MS, perm_all + m * N, ipiv_all + m * N, lane);
-                if (lane == 0 && m < nm && info != nullptr) info[first + m] = fz;
+                for (int m = 0; m < MPW; m += 2) {
+                    int fzA, fzB;
+                    prepass_getrf_x2<N, P, MS, LUONLY>(img + m * MS, perm_all + m * N, ipiv_all + m * N, lane, fzA, fzB);
+                    if (lane == 0 && info != nullptr) {
+                        if (m < nm) info[first + m] = fzA;
+                        if (m + 1 < nm) info[first + m + 1] = fzB;
+                    }
+                }
+            } else {
+#pragma unroll 1
+                for (int m = 0; m < MPW; ++m) {
+                    const int fz = prepass_getrf<T, N, P, LUONLY>(img + m * MS, perm_all + m * N, ipiv_all + m * N, lane);
+                    if (lane == 0 && m < nm && info != nullptr) info[first + m] = fz;
+                }
             }
             __syncwarp();
         } else if (MODE != kModeNone && N <= 16 && (OPT & kBulkGroupSearch) != 0) {

@@ -140,6 +140,85 @@ __device__ __forceinline__ int getrf_core(T (&a)[N], int& pos, int* __restrict__
     return first_zero;
 }
 
+// fp32: TWO matrices per call, both in the lane = row layout, their steps interleaved by hand.  One matrix is one dependent
+// chain (search -> broadcast -> update -> search ...) and a block has 12 warps, so the phase runs at about half of the
+// shuffle throughput that bounds it; warp-wide operations keep their program order, hence the interleaving is done in the
+// source.  Same recurrence per matrix as getrf_core.
+template <int N, bool LU>
+__device__ __forceinline__ void getrf_core_x2(float (&a)[N], float (&b)[N], int& posA, int& posB, int* __restrict__ ipivA,
+                                              int* __restrict__ ipivB, int lane, int& fzA, int& fzB) {
+    const bool mine = lane < N;
+    posA = posB = lane;
+    fzA = fzB = 0;
+    int pA, plA, pB, plB;
+    bool zA, zB;
+    float rownA = 1.0f / a[0], rownB = 1.0f / b[0];
+    getrf_search<float>(a[0], posA, mine, 0, lane, pA, plA, zA);
+    getrf_search<float>(b[0], posB, mine, 0, lane, pB, plB, zB);
+#pragma unroll
+    for (int k = 0; k < N; ++k) {
+        if (zA && fzA == 0) fzA = k + 1;
+        if (zB && fzB == 0) fzB = k + 1;
+        if (posA == k) posA = pA;
+        if (posB == k) posB = pB;
+        if (lane == plA) posA = k;
+        if (lane == plB) posB = k;
+        if (lane == 0) { ipivA[k] = pA + 1; ipivB[k] = pB + 1; }
+        if (k < N - 1) {
+            const int sA = plA, sB = plB;
+            const float rinvA = __shfl_sync(0xffffffffu, rownA, sA);
+            const float rinvB = __shfl_sync(0xffffffffu, rownB, sB);
+            const bool belowA = mine && posA > k, belowB = mine && posB > k;
+            const float lA = belowA ? a[k] * rinvA : 0.0f, lB = belowB ? b[k] * rinvB : 0.0f;
+            if (LU && belowA) a[k] = lA;
+            if (LU && belowB) b[k] = lB;
+            {
+                const float rA = __shfl_sync(0xffffffffu, a[k + 1], sA);
+                const float rB = __shfl_sync(0xffffffffu, b[k + 1], sB);
+                a[k + 1] = fmaf(-lA, rA, a[k + 1]);
+                b[k + 1] = fmaf(-lB, rB, b[k + 1]);
+            }
+            rownA = 1.0f / a[k + 1];
+            rownB = 1.0f / b[k + 1];
+            getrf_search<float>(a[k + 1], posA, mine, k + 1, lane, pA, plA, zA);
+            getrf_search<float>(b[k + 1], posB, mine, k + 1, lane, pB, plB, zB);
+#pragma unroll
+            for (int j = 2; j < N; ++j) {  // (constant trip count: a bound that depends on k can be left partly rolled)
+                if (j >= k + 2) {
+                    const float rA = __shfl_sync(0xffffffffu, a[j], sA);
+                    const float rB = __shfl_sync(0xffffffffu, b[j], sB);
+                    a[j] = fmaf(-lA, rA, a[j]);
+                    b[j] = fmaf(-lB, rB, b[j]);
+                }
+            }
+        }
+    }
+}
+
+// dense-image wrapper of getrf_core_x2: matrices m and m + 1 of a tile (mimg, mimg + MS)
+template <int N, int P, int MS, bool LU>
+__device__ __forceinline__ void prepass_getrf_x2(float* __restrict__ mimg, int* __restrict__ perm, int* __restrict__ ipiv_s, int lane,
+                                                 int& fzA, int& fzB) {
+    const bool mine = lane < N;
+    const float* rowA = mimg + (mine ? lane : 0) * P;
+    const float* rowB = rowA + MS;
+    float a[N], b[N];
+#pragma unroll
+    for (int j = 0; j < N; ++j) { a[j] = rowA[j]; b[j] = rowB[j]; }
+    int posA, posB;
+    getrf_core_x2<N, LU>(a, b, posA, posB, ipiv_s, ipiv_s + N, lane, fzA, fzB);
+    if (mine) { perm[posA] = lane; perm[N + posB] = lane; }
+    if constexpr (LU) {
+        __syncwarp();  // every lane has long read its rows; now the rows change places
+        if (mine) {
+            float* dA = mimg + posA * P;
+            float* dB = mimg + MS + posB * P;
+#pragma unroll
+            for (int j = 0; j < N; ++j) { dA[j] = a[j]; dB[j] = b[j]; }
+        }
+    }
+}
+
 template <typename T, int N, int P, bool LU>
 __device__ __forceinline__ int prepass_getrf(T* __restrict__ mimg, int* __restrict__ perm, int* __restrict__ ipiv_s, int lane) {
     const bool mine = lane < N;

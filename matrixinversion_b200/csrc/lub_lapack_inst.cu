@@ -1,8 +1,7 @@
-// lub_lapack_inst.cu -- instantiations and launcher of pivot_mode 3 (lub_lapack.cuh), one translation unit per
-// dtype.  Compile with -DLUB_T=float|double -DLUB_TN=f32|f64.
+// lub_lapack_inst.cu -- instantiations and launcher of pivot_mode 3 (lub_lapack.cuh; the two-phase kernels are
+// lub_bulk_kernel / lub_tma_kernel with MODE = kModeLapack), one translation unit per dtype.  Compile with -DLUB_T=float|double -DLUB_TN=f32|f64.
 #include "lub_launch.cuh"
 #include "lub_lapack.cuh"
-#include "lub_lapack2.cuh"
 
 namespace lub {
 
@@ -65,27 +64,8 @@ static cudaError_t launch_lapack_n(void* A, int32_t* ipiv, int32_t* info, long l
                               });
         }
     }
-    // N >= 17: the 2-D lane grid with bulk-copy staging (lub_lapack2.cuh) -- 13 instead of N shuffles per step; needs a
-    // 16-byte aligned batch like every bulk / TMA path.  LUB_OPT_STAGING = 1 keeps the lane = row kernel.
-    // (measured, profiles/r02_mode3_grid.jsonl: fp64 1.1-1.6x faster from N = 17 on -- N = 32: 31.7 -> 21.2 ms; fp32 only at N = 32,
-    // 10.6 -> 9.6 ms: below that the lane = row kernel's N fp32 shuffles per step cost less than the 160 instructions per step
-    // this one issues for its position bookkeeping and run-time register selects)
-    if constexpr (N >= 17 && (sizeof(T) == 8 || N == 32)) {
-        if ((x.dry_run || reinterpret_cast<uintptr_t>(A) % 16 == 0) && !(flags & kLaunchNoTma)) {
-            using L2 = Lapack2Layout<T, N>;
-            constexpr int MAXT2 = (sizeof(T) == 4) ? kMaxThreads : 384, MINB2 = (sizeof(T) == 4) ? 2 : 1;
-            static KernelCache cache2[kMaxDevices];
-            auto kern2 = lub_lapack2_kernel<T, N, LUONLY, MAXT2, MINB2>;
-            if (threads_req <= 0) x.threads = MAXT2;
-            return run_kernel(kern2, cache2[dev], x, MAXT2, [](int w) { return L2::smem_bytes(w); }, 1, 32,
-                              LUONLY ? "lub_lapack2_kernel<LUONLY>" : "lub_lapack2_kernel", [&](unsigned blocks, int smem) {
-                                  cudaError_t e = ev0 ? cudaEventRecord(ev0, stream) : cudaSuccess;
-                                  if (e != cudaSuccess) return e;
-                                  kern2<<<blocks, x.threads, smem, stream>>>(static_cast<T*>(A), ipiv, info, batch);
-                                  return cudaGetLastError();
-                              });
-        }
-    }
+    // one phase, lane = row: N <= 8, unaligned batches, LUB_OPT_STAGING = 1.  (Round 2's one-phase kernel on the 2-D lane grid,
+    // scripts/tune/lub_lapack2.cuh, is superseded by the two-phase kernels at every size it served: fp64 N = 32 21.2 -> 11.8 ms.)
     static KernelCache cache[kMaxDevices];
     auto kern = lub_lapack_kernel<T, N, LUONLY>;
     return run_kernel(kern, cache[dev], x, kMaxThreads, [](int w) { return L::smem_bytes(w); }, L::MPW, L::G,

@@ -1,3 +1,5 @@
+// SUPERSEDED (kept as a record, not part of the library): the two-phase pivot_mode 3 kernels (prepass_getrf + lub_bulk_kernel /
+// lub_tma_kernel<kModeLapack>) beat this kernel at every size it served -- profiles/r02_mode3_twophase.md.
 // lub_lapack2.cuh -- pivot_mode 3 (true partial pivoting, LAPACK getrf semantics, `ipiv` + `info`) on a 2-D lane
 // grid, for N = 17..32.  Same contract as lub_lapack.cuh (the check it is built to pass
 // is verifyLUwithPivoting, parallel_pivot/verify.hpp:157-242), another data layout:

@@ -122,7 +122,7 @@ def test_lapack_info_reports_the_first_zero_pivot():
 def test_two_phase_lapack_kernels_agree_with_the_one_phase_kernels(dtype):
     """pivot_mode 3 from n = 9 on runs the two-phase kernels (prepass_getrf: LU factorisation in the lane = row layout for the
     permutation, then the permuted-load Gauss-Jordan of modes 1 / 2; on the bulk-copy image, or the swizzled TMA image where rows
-    are whole 128-byte lines).  LUB_OPT_STAGING = 1 selects the one-phase kernels (lub_lapack.cuh / lub_lapack2.cuh): same getf2
+    are whole 128-byte lines).  LUB_OPT_STAGING = 1 selects the one-phase lane = row kernel (lub_lapack.cuh): same getf2
     recurrence, so ipiv and info must be identical -- ragged batches, singular matrices included -- the factors equal to
     rounding of the reciprocal, and the inverses within the c = 8 residual bound of each other's matrix."""
     eps = EPS[np.dtype(dtype)]
