@@ -218,7 +218,7 @@ __device__ __forceinline__ void prepass_rowpos(const T* __restrict__ img0, int* 
 constexpr int kBulkLean = 1;      // gj_eliminate_lean
 constexpr int kBulkOldSearch = 2; // the position-wise search of lub_fast.cuh (for comparison)
 constexpr int kBulkSingle = 4;    // one image per warp (no prefetch)
-constexpr int kBulkLuOnly = 64;   // pivot_mode 3 only: stop after the LU factorisation of prepass_getrf and store the factors
+constexpr int kBulkLuOnly = 64;   // factors only: pivot_mode 3 stops after prepass_getrf; modes 0 - 2 run lu_rows_dense under the known permutation
 constexpr int kBulkGetrfSingle = 128; // pivot_mode 3, fp32: one matrix at a time in the search phase (for comparison)
 constexpr int kBulkGroupSearch = 16; // N <= 16: every lane group searches its own matrix (prepass_group) instead of warp-wide searches
 
@@ -229,7 +229,6 @@ lub_bulk_kernel(T* __restrict__ A, int32_t* __restrict__ piv, long long batch, i
     constexpr bool LEAN = (OPT & kBulkLean) != 0, OLDS = (OPT & kBulkOldSearch) != 0;
     constexpr int NIMG = (OPT & kBulkSingle) ? 1 : 2;
     constexpr bool LUONLY = (OPT & kBulkLuOnly) != 0;
-    static_assert(!LUONLY || MODE == kModeLapack, "the factors-only form belongs to pivot_mode 3");
     constexpr int G = L::G, MPW = L::MPW, LR = L::LR, LC = L::LC, CH = L::CH, CPL = L::CPL, CPR = L::CPR;
     constexpr int P = L::P, MS = L::MS, ES = L::ES;
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -352,6 +351,11 @@ lub_bulk_kernel(T* __restrict__ A, int32_t* __restrict__ piv, long long batch, i
             __syncwarp();
         }
 
+        if constexpr (LUONLY && MODE != kModeLapack) {
+            // factors only, modes 0 - 2: the permutation is known; LU without a search, lane = row position (lu_rows_dense)
+#pragma unroll 1
+            for (int m = 0; m < MPW; ++m) lu_rows_dense<T, N, P>(img + m * MS, (MODE != kModeNone) ? perm_all + m * N : nullptr, lane);
+        }
         if constexpr (LUONLY && NIMG == 2) {  // factors only: the image already holds the result; fetch the next tile
             __syncwarp();
             const long long nxt = tile + tstride;

@@ -239,6 +239,48 @@ __device__ __forceinline__ int prepass_getrf(T* __restrict__ mimg, int* __restri
     return first_zero;
 }
 
+// ---- factors only, pivot modes 0 - 2 (lu_batched_factor_inplace) ------------------------------------------------------------
+// The reference's variants know their permutation before any arithmetic, so the factors "after the k-loop"
+// (templated/luBatchedInplace.cuh:99-113; rows in pivoted order, L below the diagonal with a unit diagonal implied, U on and
+// above it -- what verifyLU / verifyLUwithPivoting read, templated/verify.hpp:105-186) are an LU factorisation WITHOUT a search:
+// lane = row POSITION (the lane loads the row the permutation puts there), so the pivot row of step k sits in lane k, a
+// compile-time lane; its trailing part travels by N - 1 - k shuffles; right-looking update with the reciprocal of the pivot.
+// Same arithmetic per entry as the Gauss-Jordan kernels' elimination (fma(-l, r, a), l = a * (1 / pivot)).
+template <typename T, int N>
+__device__ __forceinline__ void lu_core_static(T (&a)[N], int lane) {
+    const bool mine = lane < N;
+#pragma unroll
+    for (int k = 0; k < N - 1; ++k) {
+        const T pv = __shfl_sync(0xffffffffu, a[k], k);
+        const T rinv = T(1) / pv;
+        const bool below = mine && lane > k;
+        const T l = below ? a[k] * rinv : T(0);
+        if (below) a[k] = l;
+#pragma unroll
+        for (int j = k + 1; j < N; ++j) {
+            const T r = __shfl_sync(0xffffffffu, a[j], k);
+            a[j] = fma(-l, r, a[j]);
+        }
+    }
+}
+// dense image (row stride P); perm == nullptr: no pivoting
+template <typename T, int N, int P>
+__device__ __forceinline__ void lu_rows_dense(T* __restrict__ mimg, const int* __restrict__ perm, int lane) {
+    const bool mine = lane < N;
+    const int row = mine ? (perm != nullptr ? perm[lane] : lane) : 0;
+    const T* rowp = mimg + row * P;
+    T a[N];
+#pragma unroll
+    for (int j = 0; j < N; ++j) a[j] = rowp[j];
+    lu_core_static<T, N>(a, lane);
+    __syncwarp();  // every lane has long read its row; now the rows change places
+    if (mine) {
+        T* dst = mimg + lane * P;
+#pragma unroll
+        for (int j = 0; j < N; ++j) dst[j] = a[j];
+    }
+}
+
 template <typename T, int N>
 struct LapackLayout {
     static constexpr int G = pow2_ceil(N), MPW = 32 / G, P = N | 1;

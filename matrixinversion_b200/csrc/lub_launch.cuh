@@ -192,7 +192,8 @@ struct BulkChoice { bool on; int gr, gc, minb, maxt, threads, opt; };
 #endif
 // `lapack`: the two-phase pivot_mode 3 kernel (MODE = kModeLapack; call with mode = kModeParallel for the block shape): every
 // N, two pivot vectors per matrix in shared memory.
-constexpr BulkChoice pick_bulk(int n, int es, int mode, bool lapack = false) {
+// `force`: every N (the factors-only kernels of modes 0 - 2).
+constexpr BulkChoice pick_bulk(int n, int es, int mode, bool lapack = false, bool force = false) {
     const Cfg c = pick_bulk_cfg(n, es, mode);
     // fp32: the sizes without 16-byte rows; fp64: every size but the two TMA / DMMA ones (N = 16, 32) -- there the
     // bulk-staged block layout also beats the rolled-step kernel of lub_v4.cuh (N = 31: 7.7 -> 5.8 ms without pivoting)
@@ -203,7 +204,7 @@ constexpr BulkChoice pick_bulk(int n, int es, int mode, bool lapack = false) {
     const bool f32_par4 = LUB_BULK_PAR4 && mode == kModeParallel && (n == 20 || n == 24 || n == 28);
     // fp32 N = 12, 16 in every mode (N = 12 serial: 0.43 -> 0.27 ms, N = 16: -3..-5 %; N = 8 loses: 0.10 -> 0.14 without pivoting)
     const bool f32_small4 = LUB_BULK_SMALL4 && (n == 12 || n == 16);
-    const bool on = lapack || (n >= LUB_BULK_MIN_N && ((es == 4) ? (n % 4 != 0 || f32_par4 || f32_small4) : !f64_off));
+    const bool on = lapack || force || (n >= LUB_BULK_MIN_N && ((es == 4) ? (n % 4 != 0 || f32_par4 || f32_small4) : !f64_off));
     if (!on) return BulkChoice{false, c.gr, c.gc, 1, kMaxThreads, 256, 0};
     const int mpw = 32 / (c.gr * c.gc);
     const int img = (mpw * n * n * es + 15) / 16 * 16 + 16;
@@ -226,6 +227,13 @@ template <typename T, int N, int MODE>
 struct BulkCfg {
     static constexpr BulkChoice c = (MODE == kModeLapack) ? pick_bulk(N, (int)sizeof(T), kModeParallel, true) : pick_bulk(N, (int)sizeof(T), MODE);
     static constexpr bool ON = kUseTma && c.on;
+    static constexpr int GR = c.gr, GC = c.gc, MINB = c.minb, MAXT = c.maxt, THREADS = c.threads, OPT = c.opt;
+};
+
+// factors only (lu_batched_factor_inplace), modes 0 - 2: the bulk-copy staged kernel at every N it is asked for
+template <typename T, int N, int MODE>
+struct BulkLuCfg {
+    static constexpr BulkChoice c = pick_bulk(N, (int)sizeof(T), MODE == kModeNone ? kModeNone : kModeParallel, false, true);
     static constexpr int GR = c.gr, GC = c.gc, MINB = c.minb, MAXT = c.maxt, THREADS = c.threads, OPT = c.opt;
 };
 
@@ -368,7 +376,53 @@ cudaError_t launch(void* A, int32_t* piv, long long batch, int threads_req, cuda
     auto start = [&]() -> cudaError_t { return ev0 ? cudaEventRecord(ev0, stream) : cudaSuccess; };
     LaunchCtx x{batch, threads_req > 0 ? threads_req : 256, stream, info, dry_run, ev0, dev};
 
-    if (flags & kLaunchLuOnly) {  // factors only: the generic kernel's LU variant (not a tuned path)
+    if (flags & kLaunchLuOnly) {
+        // Factors only.  N >= 9: the permutation is known before any arithmetic (pre-pass of the inverse kernels), so the
+        // factors are an LU factorisation without a search in the lane = row-position layout (lu_core_static, lub_lapack.cuh)
+        // on the staged image -- N = 32 fp32 parallel: 9.7 -> 3.0 ms, against 2.35 ms for the inverse
+        // (profiles/r02_lu_only.md).  Rows of whole 128-byte lines on the swizzled TMA image (no bank conflicts in
+        // the lane = row accesses), everything else on the bulk-copy image.  Smaller N, unaligned batches and
+        // LUB_OPT_STAGING = 1: the generic kernel's LU variant.
+        if constexpr (N >= 9 && kUseTma) {
+            const bool aligned = dry_run || reinterpret_cast<uintptr_t>(A) % 16 == 0;
+            if (aligned && !(flags & kLaunchNoTma)) {
+                using TCp = TmaCfg<T, N, kModeParallel>;
+                if constexpr ((N * sizeof(T)) % 128 == 0 && TCp::ON) {
+                    if (batch <= 0x7fffff00ll) {
+                        using VCp = V3Cfg<T, N, kModeParallel>;
+                        using TL = TmaLayout<T, N, TCp::GR, TCp::GC, MODE>;
+                        constexpr int NIMG = (TCp::OPT & kTmaDB) ? 2 : 1;
+                        static KernelCache cache_tlu[kMaxDevices];
+                        auto kern = lub_tma_kernel<T, N, TCp::GR, TCp::GC, MODE, (TCp::MAXT > kMaxThreads ? 1 : VCp::MINB), TCp::BSYNC, false,
+                                                   MODE == kModeNone, false, TCp::OPT | kTmaLuOnly, TCp::MAXT>;
+                        if (threads_req <= 0) x.threads = TCp::THREADS;
+                        return run_kernel(kern, cache_tlu[dev], x, TCp::MAXT, [](int w) { return TL::smem_bytes(w, NIMG); }, TL::MPW, TL::G,
+                                          "lub_tma_kernel<LUONLY>", [&](unsigned blocks, int smem) {
+                                              const CUtensorMap* map = nullptr;
+                                              cudaError_t e = cached_batch_tmap<T>(&map, A, N, batch, TL::MPW, dev);
+                                              if (e != cudaSuccess) return e;
+                                              e = start();
+                                              if (e != cudaSuccess) return e;
+                                              kern<<<blocks, x.threads, smem, stream>>>(*map, At, piv, batch, nullptr);
+                                              return cudaGetLastError();
+                                          });
+                    }
+                } else {
+                    using BC = BulkLuCfg<T, N, MODE>;
+                    using BL = BulkLayout<T, N, BC::GR, BC::GC, MODE>;
+                    static KernelCache cache_blu[kMaxDevices];
+                    auto kern = lub_bulk_kernel<T, N, BC::GR, BC::GC, MODE, BC::MINB, false, BC::OPT | kBulkLuOnly, BC::MAXT>;
+                    if (threads_req <= 0) x.threads = BC::THREADS;
+                    return run_kernel(kern, cache_blu[dev], x, BC::MAXT, [](int w) { return BL::smem_bytes(w, 2); }, BL::MPW, BL::G,
+                                      "lub_bulk_kernel<LUONLY>", [&](unsigned blocks, int smem) {
+                                          cudaError_t e = start();
+                                          if (e != cudaSuccess) return e;
+                                          kern<<<blocks, x.threads, smem, stream>>>(At, piv, batch, nullptr);
+                                          return cudaGetLastError();
+                                      });
+                }
+            }
+        }
         using AC = AutoCfg<T, N, MODE>;
         using GLU = Layout<T, N, AC::GR, AC::GC, MODE>;
         static KernelCache cache_lu[kMaxDevices];

@@ -331,6 +331,24 @@ __device__ __forceinline__ int prepass_getrf_swz(unsigned char* __restrict__ img
     return first_zero;
 }
 
+// factors only, modes 0 - 2, on the swizzled image (lu_core_static, lub_lapack.cuh): lane = row position
+template <typename T, int N>
+__device__ __forceinline__ void lu_rows_swz(unsigned char* __restrict__ img, int row0, const int* __restrict__ perm, int lane) {
+    constexpr int ES = sizeof(T), EPV = 16 / ES, RB = (N * ES + 127) / 128 * 128;
+    static_assert(N % EPV == 0, "whole 16-byte chunks per row");
+    const bool mine = lane < N;
+    const int row = mine ? (perm != nullptr ? perm[lane] : lane) : 0;
+    T a[N];
+#pragma unroll
+    for (int q = 0; q < N / EPV; ++q) ld_vec<T, EPV>(reinterpret_cast<const T*>(img + swz_byte<RB>(row0 + row, q << 4)), &a[q * EPV]);
+    lu_core_static<T, N>(a, lane);
+    __syncwarp();  // every lane has long read its row; now the rows change places
+    if (mine) {
+#pragma unroll
+        for (int q = 0; q < N / EPV; ++q) st_vec<T, EPV>(reinterpret_cast<T*>(img + swz_byte<RB>(row0 + lane, q << 4)), &a[q * EPV]);
+    }
+}
+
 // 32-byte global store (STG.256, sm_100): one full sector per lane and instruction
 __device__ __forceinline__ void st_global_256(float* p, const float* v) {
     asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]),
@@ -357,7 +375,7 @@ __device__ __forceinline__ void st_global_256(double* p, const double* v) {
 // to the very end, get the prefetch that PF gives the no-pivot path.  MAXT = threads the kernel is compiled
 // for: 16 KB per warp means 12 warps per SM (one 384-thread block, up to 168 registers per thread).
 constexpr int kTmaLean = 1, kTmaDB = 2, kTmaFused = 4;
-constexpr int kTmaLuOnly = 8;  // pivot_mode 3 only: stop after the LU factorisation of prepass_getrf and store the factors
+constexpr int kTmaLuOnly = 8;  // factors only: pivot_mode 3 stops after prepass_getrf; modes 0 - 2 run lu_rows_swz under the known permutation
 template <typename T, int N, int GR, int GC, int MODE, int MINB = 2, bool BSYNC = true, bool PF = false, bool OUTIMG = false,
           bool ST256 = false, int OPT = 0, int MAXT = kMaxThreads>
 __global__ void __launch_bounds__(MAXT, MINB)
@@ -367,7 +385,6 @@ lub_tma_kernel(const __grid_constant__ CUtensorMap tmap, T* __restrict__ A, int3
     static_assert(!OUTIMG || (MODE == kModeNone && !PF), "OUTIMG is the no-pivot output path without in-place prefetch");
     constexpr bool VIA_IMG = (MODE != kModeNone) || OUTIMG;  // results go through the image and a bulk store
     constexpr bool LEAN = (OPT & kTmaLean) != 0, DB = (OPT & kTmaDB) != 0, LUONLY = (OPT & kTmaLuOnly) != 0;
-    static_assert(!LUONLY || MODE == kModeLapack, "the factors-only form belongs to pivot_mode 3");
     static_assert(!DB || (VIA_IMG && !PF), "DB is the double-buffered form of the image-output path");
     constexpr int NIMG = DB ? 2 : 1;
     using L = TmaLayout<T, N, GR, GC, MODE>;
@@ -459,6 +476,10 @@ lub_tma_kernel(const __grid_constant__ CUtensorMap tmap, T* __restrict__ A, int3
             __syncwarp();
         }
 
+        if constexpr (LUONLY && MODE != kModeLapack) {
+#pragma unroll 1
+            for (int m = 0; m < MPW; ++m) lu_rows_swz<T, N>(img, m * N, (MODE != kModeNone) ? perm_all + m * N : nullptr, lane);
+        }
         if constexpr (LUONLY) {  // factors only: the image already holds the result; fetch the next tile and store this one
             if (DB) {
                 const long long nxt = tile + tstride;

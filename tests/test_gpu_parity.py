@@ -355,6 +355,64 @@ def test_lu_only_factors(dtype):
     assert np.array_equal(X1, X2) and np.array_equal(p1, p2)
 
 
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_lu_only_fast_kernels_agree_with_the_generic_kernel(dtype):
+    """lu_batched_factor_inplace from n = 9 on runs on the staged image of the inverse kernels (permutation from their
+    pre-pass, then an LU factorisation without a search in the lane = row-position layout: lu_core_static); LUB_OPT_STAGING = 1
+    selects the generic kernel's LU variant.  Same pivot sequence, so: permutation vectors identical, factors equal to
+    rounding (different operation order), ragged batches and batches smaller than a warp tile included; at full size the
+    factors of 200,000 matrices pass the reference's verifyLU / verifyLUwithPivoting predicate (templated/verify.hpp:105-186,
+    parallel_pivot/verify.hpp:157-242) as often as the generic kernel's."""
+    eps = EPS[np.dtype(dtype)]
+    for n in (9, 13, 16, 18, 20, 24, 27, 31, 32):
+        for mode in MODES:
+            name = lub.kernel_name(n, mode, dtype)       # (the inverse kernel of the configuration, for the record)
+            for batch in (1003, 3):
+                A = synthetic(n, batch, dtype, dominant=(mode == 0))
+                dA = torch.from_numpy(A).cuda()
+                piv = torch.full((batch, n), -1, dtype=torch.int32, device="cuda")
+                lub.lu_batched_factor_inplace(dA, piv, mode)
+                lub.set_option("staging", 1)
+                try:
+                    dB = torch.from_numpy(A).cuda()
+                    pivB = torch.full((batch, n), -1, dtype=torch.int32, device="cuda")
+                    lub.lu_batched_factor_inplace(dB, pivB, mode)
+                finally:
+                    lub.set_option("staging", 0)
+                torch.cuda.synchronize()
+                assert torch.equal(piv, pivB), (n, mode, batch, name)
+                LU, LUg = dA.cpu().numpy().astype(np.float64), dB.cpu().numpy().astype(np.float64)
+                good = np.isfinite(LUg).all(axis=(1, 2))
+                L = np.tril(LUg, -1) + np.eye(n)
+                U = np.triu(LUg)
+                bound = 4.0 * n * eps * (np.abs(L) @ np.abs(U)) + 1e-300
+                Lf = np.tril(LU, -1) + np.eye(n)
+                assert np.all((np.abs(Lf @ np.triu(LU) - L @ U) <= bound)[good]), (n, mode, batch)
+    n = 32
+    tdt = torch.float32 if dtype == np.float32 else torch.float64
+    g = torch.Generator(device="cuda").manual_seed(11)
+    A0 = torch.rand((200_000, n, n), generator=g, device="cuda", dtype=tdt)
+    for mode in (1, 2):
+        dA = A0.clone()
+        piv = torch.zeros((200_000, n), dtype=torch.int32, device="cuda")
+        lub.lu_batched_factor_inplace(dA, piv, mode)
+        lub.set_option("staging", 1)
+        try:
+            dB = A0.clone()
+            pivB = torch.zeros_like(piv)
+            lub.lu_batched_factor_inplace(dB, pivB, mode)
+        finally:
+            lub.set_option("staging", 0)
+        torch.cuda.synchronize()
+        assert torch.equal(piv, pivB), mode
+        sl = slice(0, 20_000)
+        Ah = A0[sl].cpu().numpy()
+        ok_f = lub.verify_lu(Ah, dA[sl].cpu().numpy(), piv[sl].cpu().numpy())[0]
+        ok_g = lub.verify_lu(Ah, dB[sl].cpu().numpy(), pivB[sl].cpu().numpy())[0]
+        assert abs(ok_f - ok_g) <= 20_000 * 0.01, (mode, ok_f, ok_g)
+
+
 def test_numthreads_knob_and_host_pipeline_are_bitwise_equivalent():
     for n, dtype in ((6, np.float32), (18, np.float32), (32, np.float32), (12, np.float64), (32, np.float64)):
         A = synthetic(n, 1001, dtype)
