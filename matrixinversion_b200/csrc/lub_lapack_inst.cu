@@ -30,12 +30,15 @@ static cudaError_t launch_lapack_n(void* A, int32_t* ipiv, int32_t* info, long l
         using VC = V3Cfg<T, N, kModeParallel>;
         using TL = TmaLayout<T, N, TC::GR, TC::GC, kModeLapack>;
         if ((x.dry_run || reinterpret_cast<uintptr_t>(A) % 16 == 0) && batch <= 0x7fffff00ll && !(flags & kLaunchNoTma)) {
-            constexpr int NIMG = (TC::OPT & kTmaDB) ? 2 : 1;
+            // factors only, fp32: one image per warp at 24 warps per SM (lu_hi_occupancy, lub_launch.cuh)
+            constexpr bool HI = LUONLY && sizeof(T) == 4;
+            constexpr int TOPT = HI ? (TC::OPT & ~kTmaDB) : TC::OPT, TMAXT = HI ? 768 : TC::MAXT;
+            constexpr int NIMG = (TOPT & kTmaDB) ? 2 : 1;
             static KernelCache cache4[kMaxDevices];
-            auto kern4 = lub_tma_kernel<T, N, TC::GR, TC::GC, kModeLapack, (TC::MAXT > kMaxThreads ? 1 : VC::MINB), TC::BSYNC, false, false, false,
-                                        TC::OPT | (LUONLY ? kTmaLuOnly : 0), TC::MAXT>;
-            if (threads_req <= 0) x.threads = TC::THREADS;
-            return run_kernel(kern4, cache4[dev], x, TC::MAXT, [](int w) { return TL::smem_bytes(w, NIMG); }, TL::MPW, TL::G,
+            auto kern4 = lub_tma_kernel<T, N, TC::GR, TC::GC, kModeLapack, (TMAXT > kMaxThreads ? 1 : VC::MINB), TC::BSYNC, false, false, false,
+                                        TOPT | (LUONLY ? kTmaLuOnly : 0), TMAXT>;
+            if (threads_req <= 0) x.threads = HI ? 768 : TC::THREADS;
+            return run_kernel(kern4, cache4[dev], x, TMAXT, [](int w) { return TL::smem_bytes(w, NIMG); }, TL::MPW, TL::G,
                               LUONLY ? "lub_tma_kernel<getrf, LUONLY>" : "lub_tma_kernel<getrf>", [&](unsigned blocks, int smem) {
                                   const CUtensorMap* map = nullptr;
                                   cudaError_t e = cached_batch_tmap<T>(&map, A, N, batch, TL::MPW, dev);
@@ -53,9 +56,12 @@ static cudaError_t launch_lapack_n(void* A, int32_t* ipiv, int32_t* info, long l
         const bool ok = x.dry_run || reinterpret_cast<uintptr_t>(A) % 16 == 0 || (BL::CH == 1 && reinterpret_cast<uintptr_t>(A) % sizeof(T) == 0);
         if (ok && !(flags & kLaunchNoTma)) {
             static KernelCache cache3[kMaxDevices];
-            auto kern3 = lub_bulk_kernel<T, N, BC::GR, BC::GC, kModeLapack, BC::MINB, false, BC::OPT | (LUONLY ? kBulkLuOnly : 0), BC::MAXT>;
-            if (threads_req <= 0) x.threads = BC::THREADS;
-            return run_kernel(kern3, cache3[dev], x, BC::MAXT, [](int w) { return BL::smem_bytes(w, 2); }, BL::MPW, BL::G,
+            constexpr bool HI = LUONLY && sizeof(T) == 4 && lu_hi_occupancy(N, 4);  // factors only, fp32: 24 warps, one image each
+            constexpr int BMAXT = HI ? 768 : BC::MAXT, BMINB = HI ? 1 : BC::MINB, BNIMG = HI ? 1 : 2;
+            auto kern3 = lub_bulk_kernel<T, N, BC::GR, BC::GC, kModeLapack, BMINB, false,
+                                         BC::OPT | (LUONLY ? kBulkLuOnly : 0) | (HI ? kBulkSingle : 0), BMAXT>;
+            if (threads_req <= 0) x.threads = HI ? 768 : BC::THREADS;
+            return run_kernel(kern3, cache3[dev], x, BMAXT, [](int w) { return BL::smem_bytes(w, BNIMG); }, BL::MPW, BL::G,
                               LUONLY ? "lub_bulk_kernel<getrf, LUONLY>" : "lub_bulk_kernel<getrf>", [&](unsigned blocks, int smem) {
                                   cudaError_t e = ev0 ? cudaEventRecord(ev0, stream) : cudaSuccess;
                                   if (e != cudaSuccess) return e;

@@ -231,10 +231,21 @@ struct BulkCfg {
 };
 
 // factors only (lu_batched_factor_inplace), modes 0 - 2: the bulk-copy staged kernel at every N it is asked for
+// The lane = row factorisation needs ~80 registers, not the 128-168 of the Gauss-Jordan phase, and it is bound by the latency of
+// its shuffle chain: 24 warps per SM with ONE image per warp (no prefetch; the other warps cover the load) beat 12 warps
+// with two (profiles/r02_tune_lu_only_occupancy.jsonl: fp32 N = 31 3.39 -> 2.62 ms, N = 24 2.01 -> 1.78; fp64 N = 31 5.89 -> 5.35
+// as three 256-thread blocks).  HI_F32 also serves the factors-only form of pivot_mode 3 (fp64 there: spills, slower).
+constexpr bool lu_hi_occupancy(int n, int es) { return es == 4 ? n >= 17 : n >= 21; }
 template <typename T, int N, int MODE>
 struct BulkLuCfg {
     static constexpr BulkChoice c = pick_bulk(N, (int)sizeof(T), MODE == kModeNone ? kModeNone : kModeParallel, false, true);
-    static constexpr int GR = c.gr, GC = c.gc, MINB = c.minb, MAXT = c.maxt, THREADS = c.threads, OPT = c.opt;
+    static constexpr bool HI = lu_hi_occupancy(N, (int)sizeof(T));
+    static constexpr int GR = c.gr, GC = c.gc, MINB = HI ? 1 : c.minb, MAXT = HI ? 768 : c.maxt;
+    static constexpr int THREADS = HI ? (sizeof(T) == 4 ? 768 : 256) : c.threads, NIMG = HI ? 1 : 2;
+    // largest block the launcher accepts (and sizes the shared-memory opt-in for): fp64 is compiled for 768 threads only to get
+    // the 80-register budget that lets three 256-thread blocks share an SM
+    static constexpr int CAP = HI ? THREADS : c.maxt;
+    static constexpr int OPT = c.opt | (HI ? kBulkSingle : 0);
 };
 
 // Which configurations run the TMA-staged kernel (lub_tma.cuh), on which lane grid and with or without
@@ -276,7 +287,7 @@ struct TmaCfg {
 };
 
 constexpr int kMaxDevices = 64;
-constexpr int kMaxWarps = 16;
+constexpr int kMaxWarps = 32;
 
 // Per-(kernel instantiation, device) launch facts, filled once and read by any number of host threads
 // (thread-safe for distinct streams / devices).  The dynamic shared memory opt-in is set ONCE,
@@ -391,12 +402,14 @@ cudaError_t launch(void* A, int32_t* piv, long long batch, int threads_req, cuda
                     if (batch <= 0x7fffff00ll) {
                         using VCp = V3Cfg<T, N, kModeParallel>;
                         using TL = TmaLayout<T, N, TCp::GR, TCp::GC, MODE>;
-                        constexpr int NIMG = (TCp::OPT & kTmaDB) ? 2 : 1;
+                        constexpr bool HI = sizeof(T) == 4;  // one image per warp, 24 warps per SM (see BulkLuCfg)
+                        constexpr int TOPT = HI ? (TCp::OPT & ~kTmaDB) : TCp::OPT, TMAXT = HI ? 768 : TCp::MAXT;
+                        constexpr int NIMG = (TOPT & kTmaDB) ? 2 : 1;
                         static KernelCache cache_tlu[kMaxDevices];
-                        auto kern = lub_tma_kernel<T, N, TCp::GR, TCp::GC, MODE, (TCp::MAXT > kMaxThreads ? 1 : VCp::MINB), TCp::BSYNC, false,
-                                                   MODE == kModeNone, false, TCp::OPT | kTmaLuOnly, TCp::MAXT>;
-                        if (threads_req <= 0) x.threads = TCp::THREADS;
-                        return run_kernel(kern, cache_tlu[dev], x, TCp::MAXT, [](int w) { return TL::smem_bytes(w, NIMG); }, TL::MPW, TL::G,
+                        auto kern = lub_tma_kernel<T, N, TCp::GR, TCp::GC, MODE, (TMAXT > kMaxThreads ? 1 : VCp::MINB), TCp::BSYNC, false,
+                                                   MODE == kModeNone, false, TOPT | kTmaLuOnly, TMAXT>;
+                        if (threads_req <= 0) x.threads = HI ? 768 : TCp::THREADS;
+                        return run_kernel(kern, cache_tlu[dev], x, TMAXT, [](int w) { return TL::smem_bytes(w, NIMG); }, TL::MPW, TL::G,
                                           "lub_tma_kernel<LUONLY>", [&](unsigned blocks, int smem) {
                                               const CUtensorMap* map = nullptr;
                                               cudaError_t e = cached_batch_tmap<T>(&map, A, N, batch, TL::MPW, dev);
@@ -413,7 +426,7 @@ cudaError_t launch(void* A, int32_t* piv, long long batch, int threads_req, cuda
                     static KernelCache cache_blu[kMaxDevices];
                     auto kern = lub_bulk_kernel<T, N, BC::GR, BC::GC, MODE, BC::MINB, false, BC::OPT | kBulkLuOnly, BC::MAXT>;
                     if (threads_req <= 0) x.threads = BC::THREADS;
-                    return run_kernel(kern, cache_blu[dev], x, BC::MAXT, [](int w) { return BL::smem_bytes(w, 2); }, BL::MPW, BL::G,
+                    return run_kernel(kern, cache_blu[dev], x, BC::CAP, [](int w) { return BL::smem_bytes(w, BC::NIMG); }, BL::MPW, BL::G,
                                       "lub_bulk_kernel<LUONLY>", [&](unsigned blocks, int smem) {
                                           cudaError_t e = start();
                                           if (e != cudaSuccess) return e;

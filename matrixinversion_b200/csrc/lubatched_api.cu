@@ -67,6 +67,9 @@ int fail(int code, const std::string& msg) {
 }
 int cuda_fail(cudaError_t e, const char* where) {
     g_err = std::string(where) + ": " + cudaGetErrorString(e);
+    // a non-sticky error stays in the runtime's last-error slot until it is read: clear it, or the next launch's
+    // cudaGetLastError() would report this failure again
+    (void)cudaGetLastError();
     return (e == cudaErrorNoDevice || e == cudaErrorInsufficientDriver) ? LUB_ERR_NO_DEVICE : LUB_ERR_CUDA;
 }
 #define CU(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return cuda_fail(e_, #call); } while (0)

@@ -1,0 +1,6 @@
+#!/bin/bash
+# after the high-occupancy factors-only kernels: whole GPU suite, smoke, factors-only timing
+mkdir -p gpurun_out
+(time timeout 1500 python -m pytest tests -m gpu -q) > gpurun_out/ab_pytest.log 2>&1; tail -8 gpurun_out/ab_pytest.log
+timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/ab_smoke.log 2>&1; tail -3 gpurun_out/ab_smoke.log
+bash scripts/gpu_r2_lu.sh
