@@ -22,6 +22,7 @@ ap.add_argument("--threads", type=int, default=0)
 ap.add_argument("--out", default="")
 ap.add_argument("--staging", type=int, default=0, help="LUB_OPT_STAGING: 0 = library choice, 1 = LSU staging (no TMA / bulk copies)")
 ap.add_argument("--ab", action="store_true", help="time every size with both staging settings, side by side")
+ap.add_argument("--lu", action="store_true", help="also time the factors-only entry point (lu_batched_factor_inplace) of the mode")
 a = ap.parse_args()
 tdt = torch.float32 if a.dtype == "f32" else torch.float64
 es = 4 if a.dtype == "f32" else 8
@@ -63,6 +64,15 @@ for n in [int(x) for x in a.ns.split(",")]:
     if ms_lsu is not None:
         row["ms_lsu_staging"] = ms_lsu
     row["gflops_2n3"] = 2 * n ** 3 * a.batch / ms / 1e6
+    if a.lu:
+        t3 = []
+        for i in range(a.iters + 1):
+            A.copy_(orig)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); lub.lu_batched_factor_inplace(A, None, a.mode); e1.record()
+            torch.cuda.synchronize()
+            if i: t3.append(e0.elapsed_time(e1))
+        row["lu_only_ms"] = min(t3)
     if a.cublas:
         C = _lib.cublas_lib()
         dst = torch.empty_like(A)
@@ -73,7 +83,9 @@ for n in [int(x) for x in a.ns.split(",")]:
             rc = C.lu_batched_cublas_baseline(A.data_ptr(), dst.data_ptr(), n, a.batch, 0 if a.dtype == "f32" else 1,
                                               0 if a.mode == "none" else 1, ctypes.byref(t1), ctypes.byref(t2))
             assert rc == 0
-            best = min(best, t1.value + t2.value)
+            if t1.value + t2.value < best:
+                best = t1.value + t2.value
+                row["cublas_getrf_ms"] = t1.value
         row["cublas_ms"] = best
         row["speedup_vs_cublas"] = best / ms
         del dst
