@@ -309,6 +309,13 @@ lub_bulk_kernel(T* __restrict__ A, int32_t* __restrict__ piv, long long batch, i
         __syncwarp();
 
         T* img = reinterpret_cast<T*>(buf + mis);
+        if (nm < MPW) {
+            // last tile of the batch: the matrices past its end were never loaded.  Their pivot search runs along with the
+            // others (its result is discarded), and on stale shared-memory contents two lanes can claim one position -- a
+            // write-write race on a scratch entry that compute-sanitizer reports.  Zeros make that search deterministic.
+            for (int x = nm * MS + lane; x < MPW * MS; x += 32) img[x] = T(0);
+            __syncwarp();
+        }
         T* mimg = img + ml * MS;
         int* perm = perm_all + ml * N;
         if constexpr (MODE == kModeLapack) {
