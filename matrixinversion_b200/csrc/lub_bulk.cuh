@@ -358,7 +358,34 @@ lub_bulk_kernel(T* __restrict__ A, int32_t* __restrict__ piv, long long batch, i
             __syncwarp();
         }
 
-        if constexpr (LUONLY && MODE != kModeLapack) {
+        if constexpr (LUONLY && MODE != kModeLapack && G == 1) {
+            // factors only, one lane per matrix (N <= 8 fp32, N <= 6 fp64): the lane loads its matrix with the rows permuted,
+            // factorises it in its own registers -- no exchange at all -- and writes it back in place
+            static_assert(LR == N && LC == N, "one lane holds the whole matrix");
+            T a[N][N];
+#pragma unroll
+            for (int i = 0; i < N; ++i) {
+                const T* rowp = mimg + ((MODE != kModeNone) ? perm[i] : i) * P;
+#pragma unroll
+                for (int q = 0; q < CPR; ++q) ld_vec<T, CH>(rowp + q * CH, &a[i][q * CH]);
+            }
+#pragma unroll
+            for (int k = 0; k < N - 1; ++k) {
+                const T rinv = T(1) / a[k][k];
+#pragma unroll
+                for (int i = k + 1; i < N; ++i) {
+                    const T l = a[i][k] * rinv;
+                    a[i][k] = l;
+#pragma unroll
+                    for (int j = k + 1; j < N; ++j) a[i][j] = fma(-l, a[k][j], a[i][j]);
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < N; ++i) {
+#pragma unroll
+                for (int q = 0; q < CPR; ++q) st_vec<T, CH>(mimg + i * P + q * CH, &a[i][q * CH]);
+            }
+        } else if constexpr (LUONLY && MODE != kModeLapack) {
             // factors only, modes 0 - 2: the permutation is known; LU without a search, lane = row position (lu_rows_dense)
 #pragma unroll 1
             for (int m = 0; m < MPW; ++m) lu_rows_dense<T, N, P>(img + m * MS, (MODE != kModeNone) ? perm_all + m * N : nullptr, lane);

@@ -14,7 +14,7 @@ def t(fn, it=3):
     return best
 B=1_000_000
 for dt in (torch.float32, torch.float64):
-    for n in (8, 16, 18, 24, 31, 32):
+    for n in [int(x) for x in __import__("os").environ.get("LU_NS", "8,16,18,24,31,32").split(",")]:
         g=torch.Generator(device="cuda").manual_seed(n)
         A0=torch.rand((B,n,n),generator=g,device="cuda",dtype=dt)
         A0d=A0 + n*torch.eye(n,device="cuda",dtype=dt)

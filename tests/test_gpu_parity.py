@@ -365,7 +365,7 @@ def test_lu_only_fast_kernels_agree_with_the_generic_kernel(dtype):
     factors of 200,000 matrices pass the reference's verifyLU / verifyLUwithPivoting predicate (templated/verify.hpp:105-186,
     parallel_pivot/verify.hpp:157-242) as often as the generic kernel's."""
     eps = EPS[np.dtype(dtype)]
-    for n in (9, 13, 16, 18, 20, 24, 27, 31, 32):
+    for n in (2, 5, 6, 8, 9, 13, 16, 18, 20, 24, 27, 31, 32):   # n <= 8 (fp64: <= 6): one lane factorises a whole matrix
         for mode in MODES:
             name = lub.kernel_name(n, mode, dtype)       # (the inverse kernel of the configuration, for the record)
             for batch in (1003, 3):
