@@ -27,6 +27,7 @@
 #pragma once
 #include "lub_tma.cuh"
 #include "lub_lapack.cuh"
+#include "lub_interleaved.cuh"
 
 namespace lub {
 
@@ -231,6 +232,8 @@ lub_bulk_kernel(T* __restrict__ A, int32_t* __restrict__ piv, long long batch, i
     constexpr bool LUONLY = (OPT & kBulkLuOnly) != 0;
     constexpr int G = L::G, MPW = L::MPW, LR = L::LR, LC = L::LC, CH = L::CH, CPL = L::CPL, CPR = L::CPR;
     constexpr int P = L::P, MS = L::MS, ES = L::ES;
+    constexpr bool LANE3 = MODE == kModeLapack && G == 1 && !LUONLY;  // pivot_mode 3 with one lane per matrix
+    constexpr bool IMG_DONE = LUONLY || LANE3;                        // the result is in the image before the Gauss-Jordan phase
     extern __shared__ __align__(16) unsigned char smem_raw[];
 
     const int lane = threadIdx.x & 31;
@@ -318,7 +321,72 @@ lub_bulk_kernel(T* __restrict__ A, int32_t* __restrict__ piv, long long batch, i
         }
         T* mimg = img + ml * MS;
         int* perm = perm_all + ml * N;
-        if constexpr (MODE == kModeLapack) {
+        if constexpr (LANE3) {
+            // pivot_mode 3, one lane per matrix (N <= 8 fp32, N <= 6 fp64): the whole inversion in the lane's own registers --
+            // invert_in_registers (lub_interleaved.cuh), the arithmetic of lub_lapack_kernel operation for operation, so the
+            // results are bitwise those of the lane = row kernel and of the batch-interleaved layout
+            T a[N][N];
+#pragma unroll
+            for (int i = 0; i < N; ++i) {
+#pragma unroll
+                for (int q = 0; q < CPR; ++q) ld_vec<T, CH>(mimg + i * P + q * CH, &a[i][q * CH]);
+            }
+            int pv[N];
+            const int fz = invert_in_registers<T, N, kModeLapack>(a, pv);
+#pragma unroll
+            for (int i = 0; i < N; ++i) {
+#pragma unroll
+                for (int q = 0; q < CPR; ++q) st_vec<T, CH>(mimg + i * P + q * CH, &a[i][q * CH]);
+            }
+#pragma unroll
+            for (int k = 0; k < N; ++k) ipiv_all[ml * N + k] = pv[k];
+            if (ml < nm && info != nullptr) info[first + ml] = fz;
+            __syncwarp();
+        } else if constexpr (MODE == kModeLapack && G == 1) {
+            // pivot_mode 3, factors only, one lane per matrix: getf2 in the lane's own registers -- isamax (first maximum), row
+            // interchange by conditional swaps, reciprocal scaling, fma(-l, r, a): the recurrence of lub_lapack_kernel<LUONLY>
+            using UB = typename FpBits<T>::U;
+            T a[N][N];
+#pragma unroll
+            for (int i = 0; i < N; ++i) {
+#pragma unroll
+                for (int q = 0; q < CPR; ++q) ld_vec<T, CH>(mimg + i * P + q * CH, &a[i][q * CH]);
+            }
+            int fz = 0;
+#pragma unroll
+            for (int k = 0; k < N; ++k) {
+                int p = k;
+                UB best = FpBits<T>::absbits(a[k][k]);
+#pragma unroll
+                for (int i = k + 1; i < N; ++i) {
+                    const UB v = FpBits<T>::absbits(a[i][k]);
+                    if (v > best) { best = v; p = i; }
+                }
+                if (best == UB(0) && fz == 0) fz = k + 1;
+                ipiv_all[ml * N + k] = p + 1;
+#pragma unroll
+                for (int i = k + 1; i < N; ++i) {
+                    const bool c = (p == i);
+#pragma unroll
+                    for (int j = 0; j < N; ++j) cswap(c, a[k][j], a[i][j]);
+                }
+                const T rinv = T(1) / a[k][k];
+#pragma unroll
+                for (int i = k + 1; i < N; ++i) {
+                    const T l = a[i][k] * rinv;
+                    a[i][k] = l;
+#pragma unroll
+                    for (int j = k + 1; j < N; ++j) a[i][j] = fma(-l, a[k][j], a[i][j]);
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < N; ++i) {
+#pragma unroll
+                for (int q = 0; q < CPR; ++q) st_vec<T, CH>(mimg + i * P + q * CH, &a[i][q * CH]);
+            }
+            if (ml < nm && info != nullptr) info[first + ml] = fz;
+            __syncwarp();
+        } else if constexpr (MODE == kModeLapack) {
             // true partial pivoting: the permutation comes out of an LU factorisation of the staged matrix (prepass_getrf)
             if constexpr (sizeof(T) == 4 && MPW >= 2 && N <= 20 && (OPT & kBulkGetrfSingle) == 0) {
                 // fp32, N <= 20: two matrices of the tile at a time, their steps interleaved (getrf_core_x2): -5..-10 %; from
@@ -390,7 +458,7 @@ lub_bulk_kernel(T* __restrict__ A, int32_t* __restrict__ piv, long long batch, i
 #pragma unroll 1
             for (int m = 0; m < MPW; ++m) lu_rows_dense<T, N, P>(img + m * MS, (MODE != kModeNone) ? perm_all + m * N : nullptr, lane);
         }
-        if constexpr (LUONLY && NIMG == 2) {  // factors only: the image already holds the result; fetch the next tile
+        if constexpr (IMG_DONE && NIMG == 2) {  // the image already holds the result; fetch the next tile
             __syncwarp();
             const long long nxt = tile + tstride;
             if (lane == 0 && nxt < ntiles) {
@@ -398,7 +466,7 @@ lub_bulk_kernel(T* __restrict__ A, int32_t* __restrict__ piv, long long batch, i
                 request(nxt, wbase + (cur ^ 1u) * L::IMG_BYTES, bar0 + (cur ^ 1u));
             }
         }
-        if constexpr (!LUONLY) {
+        if constexpr (!IMG_DONE) {
         // ---- registers <- image: rows permuted, LR x LC block per lane ---------------------
         T a[LR][LC];
 #pragma unroll
@@ -470,7 +538,7 @@ lub_bulk_kernel(T* __restrict__ A, int32_t* __restrict__ piv, long long batch, i
                     if (rok && ((GC * LC <= N) || (pcol[lj] >= 0))) mimg[i * P + pcol[lj]] = a[li][lj];
             }
         }
-        }  // !LUONLY
+        }  // !IMG_DONE
         fence_proxy_async();  // generic-proxy writes -> visible to the bulk-copy unit
         __syncwarp();
         {

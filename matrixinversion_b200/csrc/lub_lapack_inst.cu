@@ -50,7 +50,10 @@ static cudaError_t launch_lapack_n(void* A, int32_t* ipiv, int32_t* info, long l
                               });
         }
     }
-    if constexpr (N >= kLapackTwoPhaseMinN) {
+    // N <= 8 where one lane holds a whole matrix (fp32 N <= 8, fp64 N <= 6): the same kernel, every lane inverts / factorises
+    // its matrix in its own registers (N = 5 fp32: 0.22 -> 0.04 ms)
+    constexpr bool kOneLane = N >= 2 && N < kLapackTwoPhaseMinN && BulkCfg<T, N, kModeLapack>::GR * BulkCfg<T, N, kModeLapack>::GC == 1;
+    if constexpr (N >= kLapackTwoPhaseMinN || kOneLane) {
         using BC = BulkCfg<T, N, kModeLapack>;
         using BL = BulkLayout<T, N, BC::GR, BC::GC, kModeLapack>;
         const bool ok = x.dry_run || reinterpret_cast<uintptr_t>(A) % 16 == 0 || (BL::CH == 1 && reinterpret_cast<uintptr_t>(A) % sizeof(T) == 0);

@@ -220,7 +220,10 @@ constexpr BulkChoice pick_bulk(int n, int es, int mode, bool lapack = false, boo
     const int opt = ((es == 4 && n >= 25) ? kBulkLean : 0) | (n <= 8 ? kBulkGroupSearch : 0);
     const bool big = (es == 4) ? (n >= 25) : (n >= 21);
     if (es == 8 && mode == kModeNone && n >= 25 && n <= 30) return BulkChoice{true, c.gr, c.gc, 1, kMaxThreads, 256, opt};
-    if (minb == 1 || big) return BulkChoice{true, c.gr, c.gc, 1, 384, 384, opt};
+    // (a 384-thread block must fit the 227 KB of an SM: pivot_mode 3 with 32 small matrices per warp -- two pivot vectors
+    // each -- does not at fp64 N = 6)
+    if ((minb == 1 || big) && 64 + 12 * wb <= 232448) return BulkChoice{true, c.gr, c.gc, 1, 384, 384, opt};
+    if (minb == 1 || big) return BulkChoice{true, c.gr, c.gc, 1, kMaxThreads, 256, opt};
     return BulkChoice{true, c.gr, c.gc, minb, kMaxThreads, 256, opt};
 }
 template <typename T, int N, int MODE>
