@@ -221,6 +221,7 @@ constexpr int kBulkOldSearch = 2; // the position-wise search of lub_fast.cuh (f
 constexpr int kBulkSingle = 4;    // one image per warp (no prefetch)
 constexpr int kBulkLuOnly = 64;   // factors only: pivot_mode 3 stops after prepass_getrf; modes 0 - 2 run lu_rows_dense under the known permutation
 constexpr int kBulkGetrfSingle = 128; // pivot_mode 3, fp32: one matrix at a time in the search phase (for comparison)
+constexpr int kBulkLane = 256;    // modes 1 / 2 with one lane per matrix: the whole inversion in the lane's registers (invert_in_registers)
 constexpr int kBulkGroupSearch = 16; // N <= 16: every lane group searches its own matrix (prepass_group) instead of warp-wide searches
 
 template <typename T, int N, int GR, int GC, int MODE, int MINB = 1, bool BSYNC = false, int OPT = kBulkLean, int MAXT = kMaxThreads>
@@ -233,7 +234,9 @@ lub_bulk_kernel(T* __restrict__ A, int32_t* __restrict__ piv, long long batch, i
     constexpr int G = L::G, MPW = L::MPW, LR = L::LR, LC = L::LC, CH = L::CH, CPL = L::CPL, CPR = L::CPR;
     constexpr int P = L::P, MS = L::MS, ES = L::ES;
     constexpr bool LANE3 = MODE == kModeLapack && G == 1 && !LUONLY;  // pivot_mode 3 with one lane per matrix
-    constexpr bool IMG_DONE = LUONLY || LANE3;                        // the result is in the image before the Gauss-Jordan phase
+    // serial / parallel pivoting with one lane per matrix, the whole inversion in the lane's registers (OPT & kBulkLane)
+    constexpr bool LANE12 = (OPT & kBulkLane) != 0 && G == 1 && (MODE == kModeSerial || MODE == kModeParallel) && !LUONLY;
+    constexpr bool IMG_DONE = LUONLY || LANE3 || LANE12;              // the result is in the image before the Gauss-Jordan phase
     extern __shared__ __align__(16) unsigned char smem_raw[];
 
     const int lane = threadIdx.x & 31;
@@ -321,7 +324,26 @@ lub_bulk_kernel(T* __restrict__ A, int32_t* __restrict__ piv, long long batch, i
         }
         T* mimg = img + ml * MS;
         int* perm = perm_all + ml * N;
-        if constexpr (LANE3) {
+        if constexpr (LANE12) {
+            // invert_in_registers (lub_interleaved.cuh): search on the un-eliminated column, row interchanges by conditional swaps,
+            // the arithmetic of gj_eliminate operation for operation -- bitwise the results of the other matrix-major kernels
+            T a[N][N];
+#pragma unroll
+            for (int i = 0; i < N; ++i) {
+#pragma unroll
+                for (int q = 0; q < CPR; ++q) ld_vec<T, CH>(mimg + i * P + q * CH, &a[i][q * CH]);
+            }
+            int pv[N];
+            invert_in_registers<T, N, MODE>(a, pv);
+#pragma unroll
+            for (int i = 0; i < N; ++i) {
+#pragma unroll
+                for (int q = 0; q < CPR; ++q) st_vec<T, CH>(mimg + i * P + q * CH, &a[i][q * CH]);
+            }
+#pragma unroll
+            for (int k = 0; k < N; ++k) perm_all[ml * N + k] = pv[k];
+            __syncwarp();
+        } else if constexpr (LANE3) {
             // pivot_mode 3, one lane per matrix (N <= 8 fp32, N <= 6 fp64): the whole inversion in the lane's own registers --
             // invert_in_registers (lub_interleaved.cuh), the arithmetic of lub_lapack_kernel operation for operation, so the
             // results are bitwise those of the lane = row kernel and of the batch-interleaved layout

@@ -41,9 +41,12 @@ __device__ __forceinline__ int invert_in_registers(T (&a)[N][N], int (&piv_out)[
 #pragma unroll
         for (int k = 0; k < N; ++k) {
             int p = k;
-            // N a power of two: the tree reaches every slot and a tie stays with the lower slot = the lower row, which
-            // is find_pivot's answer; the serial search is then the cheaper equivalent (N = 8: 0.25 -> see profiles)
-            constexpr bool TREE = (MODE == kModeParallel) && ((N & (N - 1)) != 0);
+            // The tree is emulated literally for every N >= 3.  (Until late in round 2 a power-of-two N took the serial search
+            // here, on the argument that the tree then reaches every slot and a tie stays with the lower slot.  The slots
+            // are right, the tie rule is not: stride 2 moves slot 2's row into slot 0 before stride 1 compares it with slot
+            // 1, so of two equal maxima in slots 1 and 2 the HIGHER row wins -- found by the tie-heavy integer matrices of
+            // tests/test_gpu_parity.py once the matrix-major N = 8 kernel used this function.)
+            constexpr bool TREE = (MODE == kModeParallel) && N >= 3;
             if (!TREE) {
                 U best = FpBits<T>::absbits(a[k][k]);
 #pragma unroll

@@ -204,7 +204,11 @@ constexpr BulkChoice pick_bulk(int n, int es, int mode, bool lapack = false, boo
     const bool f32_par4 = LUB_BULK_PAR4 && mode == kModeParallel && (n == 20 || n == 24 || n == 28);
     // fp32 N = 12, 16 in every mode (N = 12 serial: 0.43 -> 0.27 ms, N = 16: -3..-5 %; N = 8 loses: 0.10 -> 0.14 without pivoting)
     const bool f32_small4 = LUB_BULK_SMALL4 && (n == 12 || n == 16);
-    const bool on = lapack || force || (n >= LUB_BULK_MIN_N && ((es == 4) ? (n % 4 != 0 || f32_par4 || f32_small4) : !f64_off));
+    // parallel pivoting with one lane per matrix, N = 6..8 (fp64: 6): the whole inversion in the lane's registers
+    // (invert_in_registers: search, conditional row swaps, the same arithmetic -- bitwise equal results): N = 6 0.066 -> 0.054 ms,
+    // N = 7 0.078 -> 0.076, N = 8 0.199 (lub_v3_kernel) -> 0.182, fp64 N = 6 0.102 -> 0.097 (profiles/r02_tune_lane_small_n.jsonl)
+    const bool lane12 = !lapack && !force && mode == kModeParallel && ((es == 4 && n >= 6 && n <= 8) || (es == 8 && n == 6));
+    const bool on = lapack || force || lane12 || (n >= LUB_BULK_MIN_N && ((es == 4) ? (n % 4 != 0 || f32_par4 || f32_small4) : !f64_off));
     if (!on) return BulkChoice{false, c.gr, c.gc, 1, kMaxThreads, 256, 0};
     const int mpw = 32 / (c.gr * c.gc);
     const int img = (mpw * n * n * es + 15) / 16 * 16 + 16;
@@ -217,7 +221,7 @@ constexpr BulkChoice pick_bulk(int n, int es, int mode, bool lapack = false, boo
     // (N = 15 serial: 0.52 vs 0.87 ms); from N = 25 on (two matrices per warp, 8 x 8 blocks) one 384-thread block per SM
     // with 168 registers beats two 256-thread blocks with 128 (N = 27: 1.53 vs 1.67 ms without pivoting, 2.36 vs 2.49
     // parallel); fp64 needs the 168 registers from N = 21 on (6 x 6 doubles per lane: 2.11 vs 2.82 ms)
-    const int opt = ((es == 4 && n >= 25) ? kBulkLean : 0) | (n <= 8 ? kBulkGroupSearch : 0);
+    const int opt = ((es == 4 && n >= 25) ? kBulkLean : 0) | (n <= 8 ? kBulkGroupSearch : 0) | (lane12 ? kBulkLane : 0);
     const bool big = (es == 4) ? (n >= 25) : (n >= 21);
     if (es == 8 && mode == kModeNone && n >= 25 && n <= 30) return BulkChoice{true, c.gr, c.gc, 1, kMaxThreads, 256, opt};
     // (a 384-thread block must fit the 227 KB of an SM: pivot_mode 3 with 32 small matrices per warp -- two pivot vectors

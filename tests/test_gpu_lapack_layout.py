@@ -202,6 +202,23 @@ def test_interleaved_layout_is_bitwise_equal_to_matrix_major(dtype):
                 assert torch.equal(infoI, info), (n, mode, batch)
                 back = dI.permute(2, 0, 1).contiguous()
                 assert back.dtype == tdt and torch.equal(back, dA), (n, mode, batch, float((back - dA).abs().max()))
+    # tie-heavy small-integer matrices (exact ties and zeros in every column, singular ones included): the pivot vectors of the
+    # interleaved kernel must still be the matrix-major kernels' -- which are the oracle's (test_tie_heavy_integer_matrices_pivots_exact)
+    rng = np.random.default_rng(43)
+    for n in range(2, 9):
+        A = rng.integers(-3, 4, size=(512, n, n)).astype(dtype)
+        for mode in (1, 2, 3):
+            dA = torch.from_numpy(A).cuda()
+            piv = torch.full((512, n), -1, dtype=torch.int32, device="cuda")
+            lub.lu_batched_inplace(dA, piv, mode)
+            dI = torch.from_numpy(A).cuda().permute(1, 2, 0).contiguous()
+            pivI = torch.full((512, n), -2, dtype=torch.int32, device="cuda")
+            lub.lu_batched_inplace(dI, pivI, mode, layout="interleaved")
+            torch.cuda.synchronize()
+            assert torch.equal(pivI, piv), (n, mode)
+            if mode != 3:
+                _, po = O.lu_batched(A, mode, lu_only=True)
+                assert np.array_equal(piv.cpu().numpy(), po), (n, mode)
     # a view that is not aligned for vector access still works (scalar instantiation)
     A = synthetic(4, 1024, np.float32, dominant=True)
     flat = torch.zeros(4 * 4 * 1024 + 1, device="cuda")
