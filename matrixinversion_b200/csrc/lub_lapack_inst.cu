@@ -60,7 +60,7 @@ static cudaError_t launch_lapack_n(void* A, int32_t* ipiv, int32_t* info, long l
         if (ok && !(flags & kLaunchNoTma)) {
             static KernelCache cache3[kMaxDevices];
             constexpr bool HI = LUONLY && sizeof(T) == 4 && lu_hi_occupancy(N, 4);  // factors only, fp32: 24 warps, one image each
-            constexpr int BMAXT = HI ? 768 : BC::MAXT, BMINB = HI ? 1 : BC::MINB, BNIMG = HI ? 1 : 2;
+            constexpr int BMAXT = HI ? 768 : BC::MAXT, BMINB = HI ? 1 : BC::MINB, BNIMG = (HI || (BC::OPT & kBulkSingle)) ? 1 : 2;
             auto kern3 = lub_bulk_kernel<T, N, BC::GR, BC::GC, kModeLapack, BMINB, false,
                                          BC::OPT | (LUONLY ? kBulkLuOnly : 0) | (HI ? kBulkSingle : 0), BMAXT>;
             if (threads_req <= 0) x.threads = HI ? 768 : BC::THREADS;

@@ -210,6 +210,9 @@ constexpr BulkChoice pick_bulk(int n, int es, int mode, bool lapack = false, boo
     const bool lane12 = !lapack && !force && mode == kModeParallel && ((es == 4 && n >= 6 && n <= 8) || (es == 8 && n == 6));
     const bool on = lapack || force || lane12 || (n >= LUB_BULK_MIN_N && ((es == 4) ? (n % 4 != 0 || f32_par4 || f32_small4) : !f64_off));
     if (!on) return BulkChoice{false, c.gr, c.gc, 1, kMaxThreads, 256, 0};
+    // fp64 N = 7, 8, pivot_mode 3 and the factors-only kernels: one lane per matrix as well (49 / 64 doubles per lane: one
+    // 256-thread block per SM with 255 registers, ONE image of 32 matrices per warp) -- mode 3 N = 8: 0.67 -> 0.25 ms
+    if ((lapack || force) && es == 8 && (n == 7 || n == 8)) return BulkChoice{true, 1, 1, 1, kMaxThreads, 256, kBulkGroupSearch | kBulkSingle};
     const int mpw = 32 / (c.gr * c.gc);
     const int img = (mpw * n * n * es + 15) / 16 * 16 + 16;
     const int perm = ((mode != kModeNone) ? (mpw * n * 4 + 15) / 16 * 16 : 0) * (lapack ? 2 : 1);
@@ -248,7 +251,7 @@ struct BulkLuCfg {
     static constexpr BulkChoice c = pick_bulk(N, (int)sizeof(T), MODE == kModeNone ? kModeNone : kModeParallel, false, true);
     static constexpr bool HI = lu_hi_occupancy(N, (int)sizeof(T));
     static constexpr int GR = c.gr, GC = c.gc, MINB = HI ? 1 : c.minb, MAXT = HI ? 768 : c.maxt;
-    static constexpr int THREADS = HI ? (sizeof(T) == 4 ? 768 : 256) : c.threads, NIMG = HI ? 1 : 2;
+    static constexpr int THREADS = HI ? (sizeof(T) == 4 ? 768 : 256) : c.threads, NIMG = (HI || (c.opt & kBulkSingle)) ? 1 : 2;
     // largest block the launcher accepts (and sizes the shared-memory opt-in for): fp64 is compiled for 768 threads only to get
     // the 80-register budget that lets three 256-thread blocks share an SM
     static constexpr int CAP = HI ? THREADS : c.maxt;

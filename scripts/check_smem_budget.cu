@@ -6,7 +6,7 @@
 using namespace lub;
 template <typename T, int N> void chkL() {
     using BC = BulkCfg<T, N, kModeLapack>; using BL = BulkLayout<T, N, BC::GR, BC::GC, kModeLapack>;
-    int s = BL::smem_bytes(BC::MAXT / 32, 2);
+    int s = BL::smem_bytes(BC::MAXT / 32, (BC::OPT & kBulkSingle) ? 1 : 2);
     if (s > 232448) printf("TOO BIG lapack es=%d N=%d smem=%d maxt=%d\n", (int)sizeof(T), N, s, BC::MAXT);
 }
 template <typename T, int N, int MODE> void chk() {
