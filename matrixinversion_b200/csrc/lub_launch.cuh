@@ -207,12 +207,15 @@ constexpr BulkChoice pick_bulk(int n, int es, int mode, bool lapack = false, boo
     // parallel pivoting with one lane per matrix, N = 6..8 (fp64: 6): the whole inversion in the lane's registers
     // (invert_in_registers: search, conditional row swaps, the same arithmetic -- bitwise equal results): N = 6 0.066 -> 0.054 ms,
     // N = 7 0.078 -> 0.076, N = 8 0.199 (lub_v3_kernel) -> 0.182, fp64 N = 6 0.102 -> 0.097 (profiles/r02_tune_lane_small_n.jsonl)
-    const bool lane12 = !lapack && !force && mode == kModeParallel && ((es == 4 && n >= 6 && n <= 8) || (es == 8 && n == 6));
+    // fp64 N = 7, serial and parallel, on the forced one-lane shape below: 0.244 / 0.235 -> 0.163 / 0.142 ms (N = 8: slower, not taken)
+    const bool lane12 = !lapack && !force && ((mode == kModeParallel && ((es == 4 && n >= 6 && n <= 8) || (es == 8 && n == 6))) ||
+                                              (es == 8 && n == 7 && (mode == kModeParallel || mode == kModeSerial)));
     const bool on = lapack || force || lane12 || (n >= LUB_BULK_MIN_N && ((es == 4) ? (n % 4 != 0 || f32_par4 || f32_small4) : !f64_off));
     if (!on) return BulkChoice{false, c.gr, c.gc, 1, kMaxThreads, 256, 0};
     // fp64 N = 7, 8, pivot_mode 3 and the factors-only kernels: one lane per matrix as well (49 / 64 doubles per lane: one
     // 256-thread block per SM with 255 registers, ONE image of 32 matrices per warp) -- mode 3 N = 8: 0.67 -> 0.25 ms
-    if ((lapack || force) && es == 8 && (n == 7 || n == 8)) return BulkChoice{true, 1, 1, 1, kMaxThreads, 256, kBulkGroupSearch | kBulkSingle};
+    if ((lapack || force || lane12) && es == 8 && (n == 7 || n == 8))
+        return BulkChoice{true, 1, 1, 1, kMaxThreads, 256, kBulkGroupSearch | kBulkSingle | (lane12 ? kBulkLane : 0)};
     const int mpw = 32 / (c.gr * c.gc);
     const int img = (mpw * n * n * es + 15) / 16 * 16 + 16;
     const int perm = ((mode != kModeNone) ? (mpw * n * 4 + 15) / 16 * 16 : 0) * (lapack ? 2 : 1);
@@ -528,7 +531,7 @@ cudaError_t launch(void* A, int32_t* piv, long long batch, int threads_req, cuda
         if ((fast || (BL::CH == 1 && reinterpret_cast<uintptr_t>(A) % sizeof(T) == 0)) && !no_tma) {
             auto kern = lub_bulk_kernel<T, N, BC::GR, BC::GC, MODE, BC::MINB, false, BC::OPT, BC::MAXT>;
             if (threads_req <= 0) x.threads = BC::THREADS;
-            return run_kernel(kern, cache_fast[dev], x, BC::MAXT, [](int w) { return BL::smem_bytes(w, 2); }, BL::MPW, BL::G, "lub_bulk_kernel",
+            return run_kernel(kern, cache_fast[dev], x, BC::MAXT, [](int w) { return BL::smem_bytes(w, (BC::OPT & kBulkSingle) ? 1 : 2); }, BL::MPW, BL::G, "lub_bulk_kernel",
                               [&](unsigned blocks, int smem) {
                                   cudaError_t e = start();
                                   if (e != cudaSuccess) return e;
