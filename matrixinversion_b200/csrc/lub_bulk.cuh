@@ -285,6 +285,14 @@ lub_bulk_kernel(T* __restrict__ A, int32_t* __restrict__ piv, long long batch, i
         cp_async_commit();
     };
 
+    // The matrices past the end of a partial last tile are never loaded, but their pivot search runs along with the others (its
+    // result is discarded).  On uninitialised shared memory two lanes can then claim one position of the scratch permutation -- a
+    // benign write-write race that compute-sanitizer reports (profiles/r02_sanitizer.md).  The images are therefore zeroed ONCE,
+    // here: a later partial tile finds the words of an earlier, complete tile.  (Zeroing inside the tile loop instead cost 3-7 %
+    // at fp32 N = 13..24: profiles/r02_tune_bulk.md section 7.)
+    for (int x = lane; x < NIMG * L::IMG_BYTES / 4; x += 32) reinterpret_cast<unsigned*>(wbase)[x] = 0u;
+    fence_proxy_async();
+    __syncwarp();
     unsigned iter = 0;
     if (NIMG == 2 && lane == 0) {
         const long long t0 = (long long)blockIdx.x * nwarps + warp;
@@ -315,13 +323,6 @@ lub_bulk_kernel(T* __restrict__ A, int32_t* __restrict__ piv, long long batch, i
         __syncwarp();
 
         T* img = reinterpret_cast<T*>(buf + mis);
-        if (nm < MPW) {
-            // last tile of the batch: the matrices past its end were never loaded.  Their pivot search runs along with the
-            // others (its result is discarded), and on stale shared-memory contents two lanes can claim one position -- a
-            // write-write race on a scratch entry that compute-sanitizer reports.  Zeros make that search deterministic.
-            for (int x = nm * MS + lane; x < MPW * MS; x += 32) img[x] = T(0);
-            __syncwarp();
-        }
         T* mimg = img + ml * MS;
         int* perm = perm_all + ml * N;
         if constexpr (LANE12) {
