@@ -335,7 +335,7 @@ lub_bulk_kernel(T* __restrict__ A, int32_t* __restrict__ piv, long long batch, i
                 for (int q = 0; q < CPR; ++q) ld_vec<T, CH>(mimg + i * P + q * CH, &a[i][q * CH]);
             }
             int pv[N];
-            invert_in_registers<T, N, MODE>(a, pv);
+            invert_in_registers<T, N, MODE, (MODE == kModeSerial && N == 8)>(a, pv);  // tournament argmax where measured to win
 #pragma unroll
             for (int i = 0; i < N; ++i) {
 #pragma unroll
@@ -378,13 +378,8 @@ lub_bulk_kernel(T* __restrict__ A, int32_t* __restrict__ piv, long long batch, i
             int fz = 0;
 #pragma unroll
             for (int k = 0; k < N; ++k) {
-                int p = k;
-                UB best = FpBits<T>::absbits(a[k][k]);
-#pragma unroll
-                for (int i = k + 1; i < N; ++i) {
-                    const UB v = FpBits<T>::absbits(a[i][k]);
-                    if (v > best) { best = v; p = i; }
-                }
+                UB best;
+                const int p = argmax_first<T, N, false>(a, k, best);
                 if (best == UB(0) && fz == 0) fz = k + 1;
                 ipiv_all[ml * N + k] = p + 1;
 #pragma unroll

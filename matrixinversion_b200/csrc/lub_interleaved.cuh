@@ -27,8 +27,44 @@ __device__ __forceinline__ void cswap(bool c, T& x, T& y) {
     x = t;
 }
 
+// argmax |a[i][k]|, i = k .. N - 1, FIRST maximum on ties (find_pivot, serial_pivot/luBatchedInplace.cuh:22-36; LAPACK's isamax):
+// an adjacent-pair tournament -- the left entry of a comparison always covers lower rows than the right one, and a strict "<" keeps
+// the left entry on a tie -- instead of one chain of N - k dependent compare-selects.  TOURN = false: the chain.  Measured
+// (profiles/r02_tune_lane_small_n.jsonl, r02_interleaved_vs_matrix_major.jsonl): the tournament wins where the lane is fed from a
+// staged image (matrix-major N = 8 fp32 serial: 0.167 -> 0.156 ms) and loses in the batch-interleaved kernel (its v[] / ix[]
+// arrays cost registers there: N = 7 fp32 mode 3 0.097 -> 0.147 ms), so it is a template choice.
+template <typename T, int N, bool TOURN>
+__device__ __forceinline__ int argmax_first(const T (&a)[N][N], const int k, typename FpBits<T>::U& best) {
+    using U = typename FpBits<T>::U;
+    if constexpr (!TOURN) {
+        int p = k;
+        best = FpBits<T>::absbits(a[k][k]);
+#pragma unroll
+        for (int i = k + 1; i < N; ++i) {
+            const U v = FpBits<T>::absbits(a[i][k]);
+            if (v > best) { best = v; p = i; }   // strict: the first maximum wins
+        }
+        return p;
+    }
+    U v[N];
+    int ix[N];
+#pragma unroll
+    for (int i = 0; i < N; ++i) { v[i] = (i >= k) ? FpBits<T>::absbits(a[i][k]) : U(0); ix[i] = i; }
+#pragma unroll
+    for (int w = 1; w < N; w *= 2) {
+#pragma unroll
+        for (int t = 0; t < N; ++t) {
+            if (t >= k && ((t - k) % (2 * w)) == 0 && t + w < N) {
+                if (v[t] < v[t + w]) { v[t] = v[t + w]; ix[t] = ix[t + w]; }
+            }
+        }
+    }
+    best = v[k];
+    return ix[k];
+}
+
 // One matrix, entirely in the registers of one lane.  piv_out[k]: see above.  Returns info (mode 3) or 0.
-template <typename T, int N, int MODE>
+template <typename T, int N, int MODE, bool TOURN = false>
 __device__ __forceinline__ int invert_in_registers(T (&a)[N][N], int (&piv_out)[N]) {
     using U = typename FpBits<T>::U;
     int sw[N];  // row interchanged with row k at step k (0-based; sw[k] == k: none)
@@ -48,12 +84,8 @@ __device__ __forceinline__ int invert_in_registers(T (&a)[N][N], int (&piv_out)[
             // tests/test_gpu_parity.py once the matrix-major N = 8 kernel used this function.)
             constexpr bool TREE = (MODE == kModeParallel) && N >= 3;
             if (!TREE) {
-                U best = FpBits<T>::absbits(a[k][k]);
-#pragma unroll
-                for (int i = k + 1; i < N; ++i) {
-                    const U v = FpBits<T>::absbits(a[i][k]);
-                    if (v > best) { best = v; p = i; }   // strict: lowest row wins ties
-                }
+                U best;
+                p = argmax_first<T, N, TOURN>(a, k, best);   // lowest row wins ties
             } else {
                 // find_pivot_parallel, literally: TPM = N slots, slot t seeded with row k and offered row k + 1 + t,
                 // then the halving tree with integer-divided strides (slots it never merges are dropped, Q2)
@@ -91,13 +123,8 @@ __device__ __forceinline__ int invert_in_registers(T (&a)[N][N], int (&piv_out)[
 #pragma unroll
     for (int k = 0; k < N; ++k) {
         if (MODE == kModeLapack) {
-            int p = k;
-            U best = FpBits<T>::absbits(a[k][k]);
-#pragma unroll
-            for (int i = k + 1; i < N; ++i) {
-                const U v = FpBits<T>::absbits(a[i][k]);
-                if (v > best) { best = v; p = i; }       // isamax: first maximum
-            }
+            U best;
+            const int p = argmax_first<T, N, TOURN>(a, k, best);   // isamax: first maximum
             if (best == U(0) && info == 0) info = k + 1;
             sw[k] = p;
             piv_out[k] = p + 1;

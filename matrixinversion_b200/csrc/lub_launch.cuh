@@ -209,7 +209,8 @@ constexpr BulkChoice pick_bulk(int n, int es, int mode, bool lapack = false, boo
     // N = 7 0.078 -> 0.076, N = 8 0.199 (lub_v3_kernel) -> 0.182, fp64 N = 6 0.102 -> 0.097 (profiles/r02_tune_lane_small_n.jsonl)
     // fp64 N = 7, serial and parallel, on the forced one-lane shape below: 0.244 / 0.235 -> 0.163 / 0.142 ms (N = 8: slower, not taken)
     const bool lane12 = !lapack && !force && ((mode == kModeParallel && ((es == 4 && n >= 6 && n <= 8) || (es == 8 && n == 6))) ||
-                                              (es == 8 && n == 7 && (mode == kModeParallel || mode == kModeSerial)));
+                                              (es == 8 && n == 7 && (mode == kModeParallel || mode == kModeSerial)) ||
+                                              (es == 4 && n == 8 && mode == kModeSerial));  // 0.167 -> 0.156 ms with the tournament argmax
     const bool on = lapack || force || lane12 || (n >= LUB_BULK_MIN_N && ((es == 4) ? (n % 4 != 0 || f32_par4 || f32_small4) : !f64_off));
     if (!on) return BulkChoice{false, c.gr, c.gc, 1, kMaxThreads, 256, 0};
     // fp64 N = 7, 8, pivot_mode 3 and the factors-only kernels: one lane per matrix as well (49 / 64 doubles per lane: one
