@@ -148,7 +148,9 @@ int lu_batched_get_threads(int n, int dtype);
  *   LUB_OPT_STAGING      0 = library choice (TMA bulk tensor copies into a swizzled image where rows are 128 / 256 bytes or
  *                            padded to a line, 1-D cp.async.bulk span copies into a dense image elsewhere from N = 5 on),
  *                        1 = LSU staging (128-bit loads / cp.async into a padded or dense image) for every size, and the
- *                            lane = row kernel for pivot_mode 3;
+ *                            one-phase lane = row kernel for pivot_mode 3 (library choice from n = 9 on: two phases, an LU
+ *                            factorisation for the permutation, then the Gauss-Jordan of modes 1 / 2) and the generic
+ *                            kernel for lu_batched_factor_inplace;
  *   LUB_OPT_FP64_TENSOR  fp64 N = 32, blocked elimination with DMMA rank-4 updates (csrc/lub_dmma.cuh):
  *                        0 = library choice: without pivoting only (as accurate as the unblocked elimination there);
  *                        1 = never (DFMA rank-1 updates with shuffle exchange);
