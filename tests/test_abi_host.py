@@ -233,3 +233,21 @@ def test_ipiv_to_perm_host_helper():
     bad = ipiv.copy(); bad[0, 3] = 2            # points above the diagonal: not a getrf swap list
     with pytest.raises(lub.LubError):
         lub.ipiv_to_perm(bad)
+
+
+def test_every_staged_configuration_fits_the_shared_memory_of_an_sm(tmp_path):
+    """Host-only (no GPU): scripts/check_smem_budget.cu instantiates the launch tables of the bulk-copy staged kernels -- inverse,
+    factors only, pivot_mode 3; n = 2..32, both dtypes -- and checks that none asks for more than the 227 KB of dynamic shared
+    memory an SM has (a configuration that did once: fp64 n = 6 with two pivot vectors per matrix in a 384-thread block)."""
+    import shutil
+    import subprocess
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not os.path.exists(nvcc):
+        pytest.skip("nvcc not available")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = str(tmp_path / "check_smem")
+    subprocess.check_call([nvcc, "-std=c++17", "-I" + os.path.join(root, "matrixinversion_b200", "csrc"), "-I" + os.path.join(root, "include"),
+                           "-gencode", "arch=compute_100a,code=sm_100a", os.path.join(root, "scripts", "check_smem_budget.cu"), "-o", exe],
+                          stderr=subprocess.DEVNULL)
+    out = subprocess.run([exe], capture_output=True, text=True, check=True).stdout
+    assert "TOO BIG" not in out and out.strip().endswith("done"), out
